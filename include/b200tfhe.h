@@ -1,0 +1,135 @@
+/*
+ * b200tfhe.h -- C ABI of libb200tfhe.so, the B200-native (sm_100a) drop-in for the reference's
+ * shortint keyswitch + programmable-bootstrap path.
+ *
+ * Reference: M-Bln/tfhe-rs-string (fork of tfhe-rs 0.5.0), paths relative to tfhe/src/.
+ * The reference has no plugin interface for this path: callers use inherent methods of
+ * shortint::ServerKey.  Each entry point below names the reference function(s) whose work it
+ * replaces; INTEGRATION.md shows the Rust `extern "C"` shim a maintainer adds so that
+ * ServerKey::apply_lookup_table[_assign] dispatches here.
+ *
+ * Conventions (mirroring the reference's own C API, c_api/utils.rs:3-27):
+ *   - every function returns int: 0 = success, non-zero = error (never unwinds / aborts);
+ *     b200tfhe_last_error() returns the message of the last failing call on that context;
+ *   - only plain pointers and sizes cross the ABI; ciphertext metadata (degree, noise level)
+ *     stays with the caller exactly as at shortint/server_key/mod.rs:855-856;
+ *   - all ciphertext/key layouts are the reference's flat u64 layouts, verbatim:
+ *       LWE ciphertext   [a_0 .. a_{n-1}, b]                 (entities/lwe_ciphertext.rs:598-609)
+ *       GLWE accumulator [mask polys .., body poly]          (entities/glwe_ciphertext.rs:423-433)
+ *       KSK              [in_dim][level (l first)][out_dim+1]  (entities/lwe_keyswitch_key.rs:77-108,
+ *                                                             algorithms/lwe_keyswitch_key_generation.rs:109-111)
+ *       standard BSK     [n][level 1..l][k+1 rows][k+1 polys][N] (entities/ggsw_ciphertext.rs:185-197)
+ *   - there is NO CPU fallback: without a CUDA device every call fails with an error.
+ *
+ * "host" entry points borrow host buffers for the duration of the call (H2D, compute, D2H,
+ * synchronous).  "_device" entry points take device pointers, enqueue on the context's stream
+ * and return immediately; use b200tfhe_sync() or your own event on b200tfhe_stream().
+ */
+#ifndef B200TFHE_H
+#define B200TFHE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200tfhe_ctx b200tfhe_ctx;
+
+/* shortint/parameters/mod.rs:62-76 (ClassicPBSParameters), KS->PBS order, native modulus.
+ * Supported by the kernels today: glwe_dimension = 1, polynomial_size = 2048, pbs_level = 1,
+ * ks_base_log <= 7 (PARAM_MESSAGE_2_CARRY_2_KS_PBS, shortint/parameters/mod.rs:703-717, and any
+ * parameter set of the same shape with another lwe_dimension / KS decomposition). */
+typedef struct {
+    uint32_t lwe_dimension;   /* n  */
+    uint32_t glwe_dimension;  /* k  */
+    uint32_t polynomial_size; /* N  */
+    uint32_t pbs_base_log, pbs_level;
+    uint32_t ks_base_log, ks_level;
+    uint32_t message_modulus, carry_modulus;
+} b200tfhe_params;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* Creates a context bound to CUDA device `device` (one context per GPU; one process per GPU
+ * in multi-GPU runs).  Replaces ShortintEngine's thread-local scratch (shortint/engine/mod.rs:
+ * 23-25,40-69): all scratch lives on the device and is owned by the context. */
+int b200tfhe_ctx_create(const b200tfhe_params *params, int device, b200tfhe_ctx **out);
+int b200tfhe_ctx_destroy(b200tfhe_ctx *ctx);
+int b200tfhe_last_error(const b200tfhe_ctx *ctx, char *buf, size_t buf_len);
+/* Last error of a failed b200tfhe_ctx_create (no context exists yet). */
+int b200tfhe_last_global_error(char *buf, size_t buf_len);
+
+/* ---- server key upload ---------------------------------------------------------------- */
+/* key_switching_key.as_ref() of shortint::ServerKey (shortint/server_key/mod.rs:284-297). */
+int b200tfhe_load_ksk(b200tfhe_ctx *ctx, const uint64_t *ksk, size_t n_u64);
+/* Standard-domain bootstrap key, taken where the reference still has it
+ * (shortint/engine/server_side.rs:63-86, shortint/server_key/mod.rs:951-966); converted on the
+ * GPU to this library's Fourier layout (replaces par_convert_standard_lwe_bootstrap_key_to_fourier,
+ * algorithms/lwe_bootstrap_key_conversion.rs:99+). */
+int b200tfhe_load_bsk_standard(b200tfhe_ctx *ctx, const uint64_t *bsk, size_t n_u64);
+/* Device-resident key arena (Fourier BSK || KSK || KS column sums), contiguous, so a multi-GPU
+ * launcher can broadcast it once (NCCL) instead of re-uploading: rank 0 loads keys, every rank
+ * passes its arena pointer to the collective, then non-root ranks call b200tfhe_keys_adopt(). */
+int b200tfhe_key_arena(b200tfhe_ctx *ctx, void **device_ptr, size_t *bytes);
+int b200tfhe_keys_adopt(b200tfhe_ctx *ctx);
+
+/* ---- lookup tables -------------------------------------------------------------------- */
+/* Registers a GLWE accumulator ((k+1)*N u64, as produced by generate_lookup_table /
+ * fill_accumulator, shortint/server_key/mod.rs:383-399, shortint/engine/mod.rs:72-128) and
+ * returns its id.  Content-addressed: registering the same table twice returns the same id. */
+int b200tfhe_register_lut(b200tfhe_ctx *ctx, const uint64_t *glwe_acc, uint32_t *id);
+/* Device-side fill_accumulator for a function table f(0..message_modulus*carry_modulus-1). */
+int b200tfhe_register_lut_from_table(b200tfhe_ctx *ctx, const uint64_t *table, size_t table_len, uint32_t *id);
+
+/* ---- hot path, host buffers ----------------------------------------------------------- */
+/* keyswitch_lwe_ciphertext (core_crypto/algorithms/lwe_keyswitch.rs:96-170), batched.
+ * in: batch x (k*N+1), out: batch x (n+1). */
+int b200tfhe_keyswitch_batch(b200tfhe_ctx *ctx, const uint64_t *in, uint64_t *out, size_t batch);
+/* programmable_bootstrap_lwe_ciphertext_mem_optimized (core_crypto/algorithms/
+ * lwe_programmable_bootstrapping.rs:1067-1110 -> fft64/crypto/bootstrap.rs:333-364), batched.
+ * in: batch x (n+1), lut_id: batch ids (NULL = id 0 for all), out: batch x (k*N+1). */
+int b200tfhe_pbs_batch(b200tfhe_ctx *ctx, const uint64_t *in, const uint32_t *lut_id, uint64_t *out, size_t batch);
+/* ServerKey::keyswitch_programmable_bootstrap_assign (shortint/server_key/mod.rs:783-857,
+ * classic branch, non-trivial ciphertexts; the trivial shortcut :788-791 stays on the caller's
+ * side) == apply_lookup_table_assign for PBSOrder::KeyswitchBootstrap (:465-476), batched.
+ * in/out: batch x (k*N+1); in == out allowed. */
+int b200tfhe_ks_pbs_batch(b200tfhe_ctx *ctx, const uint64_t *in, const uint32_t *lut_id, uint64_t *out, size_t batch);
+
+/* ---- hot path, device buffers (asynchronous on the context stream) -------------------- */
+int b200tfhe_keyswitch_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, size_t batch);
+int b200tfhe_pbs_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const uint32_t *d_lut_id, uint64_t *d_out, size_t batch);
+int b200tfhe_ks_pbs_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const uint32_t *d_lut_id, uint64_t *d_out, size_t batch);
+/* lwe_linear_algebra.rs (:68 add, :276 plaintext add, :556 cleartext mul, :703 sub) and the
+ * bivariate pack (shortint/server_key/bivariate_pbs.rs:173-181), one launch:
+ *   out[b] = ca[b] * x[ia[b]] + cb[b] * y[ib[b]];  out[b].body += pt[b]
+ * All pointers are device pointers; ia/ib/cb/pt/y may be NULL (identity / none). lwe_size is
+ * the number of u64 per ciphertext. */
+int b200tfhe_lwe_linear_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_x, const uint64_t *d_y,
+                                     const int32_t *d_ia, const int32_t *d_ib, const int64_t *d_ca,
+                                     const int64_t *d_cb, const uint64_t *d_pt, uint64_t *d_out,
+                                     size_t batch, size_t lwe_size);
+int b200tfhe_sync(b200tfhe_ctx *ctx);
+/* cudaStream_t of the context, as void*, so callers can record their own events on it. */
+int b200tfhe_stream(b200tfhe_ctx *ctx, void **stream);
+
+/* ---- measurement ---------------------------------------------------------------------- */
+/* When enabled, every ks / pbs kernel launch is bracketed by CUDA events on the context stream. */
+int b200tfhe_set_profiling(b200tfhe_ctx *ctx, int enabled);
+/* Accumulated device time (ms) and launch counts since the last reset; synchronises. */
+int b200tfhe_get_kernel_times(b200tfhe_ctx *ctx, double *ks_ms, uint64_t *ks_launches, double *pbs_ms,
+                              uint64_t *pbs_launches, int reset);
+/* Selects the PBS kernel variant: 0 = default (TMEM accumulator, 4 ciphertexts/CTA),
+ * 1 = shared-memory accumulator (2/CTA), 2 = TMEM, 6 ciphertexts/CTA. */
+int b200tfhe_set_pbs_variant(b200tfhe_ctx *ctx, int variant);
+
+/* ---- unit-test hooks (exercise exactly the transforms the PBS kernel uses) ------------ */
+/* out[i] += a_int[i] (x) b_torus[i] in Z[X]/(X^2048+1); host buffers, count x 2048 u64 each.
+ * Mirrors the reference's FFT product test, fft_impl/fft64/math/fft/tests.rs:82-222. */
+int b200tfhe_debug_negacyclic_mul(b200tfhe_ctx *ctx, const uint64_t *a_int, const uint64_t *b_torus,
+                                  uint64_t *out, size_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TFHE_H */

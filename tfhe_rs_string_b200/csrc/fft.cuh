@@ -1,0 +1,138 @@
+// fft.cuh -- warp-level negacyclic FFT for N = 2048 (1024 complex points), FP64, sm_100a.
+//
+// One warp transforms one polynomial.  Lane l owns the 32 folded points j = l + 32*m
+// (m = 0..31), i.e. coefficients j (real part) and j + 1024 (imaginary part): the "home layout".
+// 1024 = 32 x 32 Cooley-Tukey: a 32-point transform entirely in registers (over m), one twiddle,
+// one transposition through shared memory, and a second 32-point transform in registers.
+//
+// The negacyclic twist w_j = exp(i*pi*j/2048) (reference: Twisties::new,
+// core_crypto/fft_impl/fft64/math/fft/mod.rs:58-69) is split as w_j = A_l * C_m:
+//   C_m = exp(i*pi*m/64)    depends on the register index only -> compile-time constant
+//   A_l = exp(i*pi*l/2048)  depends on the lane only -> folded into the inter-pass twiddle table
+// so the twist costs no table traffic.  T'[k1][l] = exp(-2*pi*i*l*k1/1024) * A_l.
+//
+// Frequency k = k1 + 32*k2 ends up in lane k1, register k2: "Fourier layout" [q = k2][lane],
+// which is also how the Fourier bootstrap key is stored, so its loads are 512 B coalesced.
+// This ordering is private to this library (the reference's ordering is plan dependent,
+// fft/mod.rs:161,335-350, which is why the C ABI ingests the standard-domain BSK).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "fft_consts.h"
+
+namespace b200 {
+
+constexpr int kN = 2048;         // polynomial size
+constexpr int kHalf = 1024;      // complex points
+constexpr int kTStride = 33;     // padded row stride (in double2) of the transposition buffer
+constexpr int kTBufElems = 32 * kTStride;  // double2 elements per warp buffer (16,896 B)
+
+__device__ __constant__ double2 c_w32[16] = {B200_W32_TABLE};
+__device__ __constant__ double2 c_twm[32] = {B200_TWIST_M_TABLE};
+
+__host__ __device__ constexpr int brev5(int x) {
+    return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+}
+
+// radix-2 DIT butterfly (a, b) -> (a + w*b, a - w*b), w = W32^TW (conjugated when INV).
+// 6 FP64 instructions for a generic twiddle: two chained FMAs per component for a + w*b, then
+// a - w*b = 2a - (a + w*b) as one FMA.  4 instructions for w in {1, -i, +i}.
+template <bool INV>
+__device__ __forceinline__ void bfly(double &ar, double &ai, double &br, double &bi, const int tw) {
+    if (tw == 0) {
+        const double tr = ar - br, ti = ai - bi;
+        ar += br; ai += bi; br = tr; bi = ti;
+    } else if (tw == 8) {
+        // forward: w = -i -> w*b = (bi, -br); inverse: w = +i -> w*b = (-bi, br)
+        const double pr = INV ? -bi : bi, pi = INV ? br : -br;
+        const double tr = ar - pr, ti = ai - pi;
+        ar += pr; ai += pi; br = tr; bi = ti;
+    } else {
+        const double wr = c_w32[tw].x;
+        const double wi = INV ? -c_w32[tw].y : c_w32[tw].y;
+        double sr = fma(wr, br, ar);
+        sr = fma(-wi, bi, sr);
+        double si = fma(wr, bi, ai);
+        si = fma(wi, br, si);
+        br = fma(2.0, ar, -sr);
+        bi = fma(2.0, ai, -si);
+        ar = sr; ai = si;
+    }
+}
+
+// In-register 32-point DFT, decimation in time: input in bit-reversed register order, output in
+// natural order.  Register indices are compile-time after unrolling, so the bit reversal is free.
+template <bool INV>
+__device__ __forceinline__ void fft32_dit(double (&xr)[32], double (&xi)[32]) {
+#pragma unroll
+    for (int half = 1; half < 32; half <<= 1) {
+#pragma unroll
+        for (int base = 0; base < 32; base += 2 * half) {
+#pragma unroll
+            for (int t = 0; t < half; t++) {
+                bfly<INV>(xr[base + t], xi[base + t], xr[base + t + half], xi[base + t + half], t * (16 / half));
+            }
+        }
+    }
+}
+
+// Forward transform.  In: x[brev5(m)] = twisted-by-C_m folded point l + 32*m (A_l NOT applied).
+// Out: x[k2] = F[lane + 32*k2].  tbuf: this warp's private 32x33 double2 buffer.
+__device__ __forceinline__ void fwd1024(double (&xr)[32], double (&xi)[32], double2 *tbuf,
+                                        const double2 *__restrict__ twid, const int lane) {
+    fft32_dit<false>(xr, xi);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) {
+        const double2 t = twid[k1 * 32 + lane];
+        double2 y;
+        y.x = fma(-xi[k1], t.y, xr[k1] * t.x);
+        y.y = fma(xi[k1], t.x, xr[k1] * t.y);
+        tbuf[lane * kTStride + k1] = y;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < 32; l++) {
+        const double2 v = tbuf[l * kTStride + lane];
+        xr[brev5(l)] = v.x; xi[brev5(l)] = v.y;
+    }
+    __syncwarp();
+    fft32_dit<false>(xr, xi);
+}
+
+// Inverse transform (unnormalised; the 1/1024 is folded into the Fourier BSK).
+// In: x[brev5(k2)] = G[lane + 32*k2].  Out: x[m] = conj(A_l)-untwisted point l + 32*m; the caller
+// still has to multiply by conj(C_m).
+__device__ __forceinline__ void inv1024(double (&xr)[32], double (&xi)[32], double2 *tbuf,
+                                        const double2 *__restrict__ twid, const int lane) {
+    fft32_dit<true>(xr, xi);
+#pragma unroll
+    for (int l = 0; l < 32; l++) tbuf[lane * kTStride + l] = make_double2(xr[l], xi[l]);
+    __syncwarp();
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) {
+        const double2 v = tbuf[k1 * kTStride + lane];
+        const double2 t = twid[k1 * 32 + lane];   // multiply by conj(t)
+        xr[brev5(k1)] = fma(v.y, t.y, v.x * t.x);
+        xi[brev5(k1)] = fma(v.y, t.x, -(v.x * t.y));
+    }
+    __syncwarp();
+    fft32_dit<true>(xr, xi);
+}
+
+// multiply register m by C_m (forward twist) / conj(C_m) (inverse untwist)
+__device__ __forceinline__ void twist_m(double &r, double &i, const int m) {
+    if (m == 0) return;
+    const double cr = c_twm[m].x, ci = c_twm[m].y;
+    const double nr = fma(-i, ci, r * cr);
+    i = fma(i, cr, r * ci);
+    r = nr;
+}
+__device__ __forceinline__ void untwist_m(double &r, double &i, const int m) {
+    if (m == 0) return;
+    const double cr = c_twm[m].x, ci = c_twm[m].y;
+    const double nr = fma(i, ci, r * cr);
+    i = fma(i, cr, -(r * ci));
+    r = nr;
+}
+
+}  // namespace b200

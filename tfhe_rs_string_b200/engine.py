@@ -1,0 +1,260 @@
+"""ctypes binding of libb200tfhe.so (C ABI declared in include/b200tfhe.h)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# every symbol include/b200tfhe.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "b200tfhe_ctx_create", "b200tfhe_ctx_destroy", "b200tfhe_last_error", "b200tfhe_last_global_error",
+    "b200tfhe_load_ksk", "b200tfhe_load_bsk_standard", "b200tfhe_key_arena", "b200tfhe_keys_adopt",
+    "b200tfhe_register_lut", "b200tfhe_register_lut_from_table",
+    "b200tfhe_keyswitch_batch", "b200tfhe_pbs_batch", "b200tfhe_ks_pbs_batch",
+    "b200tfhe_keyswitch_batch_device", "b200tfhe_pbs_batch_device", "b200tfhe_ks_pbs_batch_device",
+    "b200tfhe_lwe_linear_batch_device", "b200tfhe_sync", "b200tfhe_stream",
+    "b200tfhe_set_profiling", "b200tfhe_get_kernel_times", "b200tfhe_set_pbs_variant",
+    "b200tfhe_debug_negacyclic_mul",
+]
+
+
+class B200TfheError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """b200tfhe_params == ClassicPBSParameters of the reference (shortint/parameters/mod.rs:62-76)."""
+    _fields_ = [
+        ("lwe_dimension", C.c_uint32), ("glwe_dimension", C.c_uint32), ("polynomial_size", C.c_uint32),
+        ("pbs_base_log", C.c_uint32), ("pbs_level", C.c_uint32),
+        ("ks_base_log", C.c_uint32), ("ks_level", C.c_uint32),
+        ("message_modulus", C.c_uint32), ("carry_modulus", C.c_uint32),
+    ]
+
+    @classmethod
+    def message_2_carry_2(cls):
+        """PARAM_MESSAGE_2_CARRY_2_KS_PBS (shortint/parameters/mod.rs:703-717)."""
+        return cls(742, 1, 2048, 23, 1, 3, 5, 4, 4)
+
+    @property
+    def big_lwe_size(self):
+        return self.glwe_dimension * self.polynomial_size + 1
+
+    @property
+    def small_lwe_size(self):
+        return self.lwe_dimension + 1
+
+    @property
+    def glwe_len(self):
+        return (self.glwe_dimension + 1) * self.polynomial_size
+
+
+def lib_path():
+    return os.path.join(_HERE, "libb200tfhe.so")
+
+
+def load_library():
+    """Loads libb200tfhe.so; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise B200TfheError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(path)
+    u64p, u32p, vp = C.c_void_p, C.c_void_p, C.c_void_p   # raw addresses (host or device)
+    ctx = C.c_void_p
+    sig = {
+        "b200tfhe_ctx_create": [C.POINTER(Params), C.c_int, C.POINTER(ctx)],
+        "b200tfhe_ctx_destroy": [ctx],
+        "b200tfhe_last_error": [ctx, C.c_char_p, C.c_size_t],
+        "b200tfhe_last_global_error": [C.c_char_p, C.c_size_t],
+        "b200tfhe_load_ksk": [ctx, u64p, C.c_size_t],
+        "b200tfhe_load_bsk_standard": [ctx, u64p, C.c_size_t],
+        "b200tfhe_key_arena": [ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
+        "b200tfhe_keys_adopt": [ctx],
+        "b200tfhe_register_lut": [ctx, u64p, C.POINTER(C.c_uint32)],
+        "b200tfhe_register_lut_from_table": [ctx, u64p, C.c_size_t, C.POINTER(C.c_uint32)],
+        "b200tfhe_keyswitch_batch": [ctx, u64p, u64p, C.c_size_t],
+        "b200tfhe_pbs_batch": [ctx, u64p, u32p, u64p, C.c_size_t],
+        "b200tfhe_ks_pbs_batch": [ctx, u64p, u32p, u64p, C.c_size_t],
+        "b200tfhe_keyswitch_batch_device": [ctx, u64p, u64p, C.c_size_t],
+        "b200tfhe_pbs_batch_device": [ctx, u64p, u32p, u64p, C.c_size_t],
+        "b200tfhe_ks_pbs_batch_device": [ctx, u64p, u32p, u64p, C.c_size_t],
+        "b200tfhe_lwe_linear_batch_device": [ctx, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_size_t],
+        "b200tfhe_sync": [ctx],
+        "b200tfhe_stream": [ctx, C.POINTER(C.c_void_p)],
+        "b200tfhe_set_profiling": [ctx, C.c_int],
+        "b200tfhe_get_kernel_times": [ctx, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_uint64), C.c_int],
+        "b200tfhe_set_pbs_variant": [ctx, C.c_int],
+        "b200tfhe_debug_negacyclic_mul": [ctx, u64p, u64p, u64p, C.c_size_t],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+def _ptr(x):
+    """Address of a numpy array (host) or torch tensor (host or device); None -> NULL."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous()
+        return x.data_ptr()
+    if isinstance(x, int):
+        return x
+    raise TypeError(type(x))
+
+
+class Engine:
+    """One context per GPU.  Mirrors the call surface of shortint::ServerKey for the KS+PBS path:
+    keyswitch / programmable bootstrap / apply_lookup_table, batched."""
+
+    def __init__(self, params=None, device=0):
+        self.L = load_library()
+        self.params = params or Params.message_2_carry_2()
+        self.device = device
+        h = C.c_void_p()
+        rc = self.L.b200tfhe_ctx_create(C.byref(self.params), device, C.byref(h))
+        if rc != 0:
+            buf = C.create_string_buffer(1024)
+            self.L.b200tfhe_last_global_error(buf, 1024)
+            raise B200TfheError(buf.value.decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200tfhe_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            buf = C.create_string_buffer(1024)
+            self.L.b200tfhe_last_error(self.h, buf, 1024)
+            raise B200TfheError(buf.value.decode())
+
+    # ---- keys / LUTs
+    def load_ksk(self, ksk):
+        ksk = np.ascontiguousarray(ksk, dtype=np.uint64)
+        self._check(self.L.b200tfhe_load_ksk(self.h, _ptr(ksk), ksk.size))
+
+    def load_bsk_standard(self, bsk):
+        bsk = np.ascontiguousarray(bsk, dtype=np.uint64)
+        self._check(self.L.b200tfhe_load_bsk_standard(self.h, _ptr(bsk), bsk.size))
+
+    def key_arena(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.L.b200tfhe_key_arena(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def keys_adopt(self):
+        self._check(self.L.b200tfhe_keys_adopt(self.h))
+
+    def register_lut(self, glwe_acc):
+        acc = np.ascontiguousarray(glwe_acc, dtype=np.uint64)
+        assert acc.size == self.params.glwe_len
+        i = C.c_uint32()
+        self._check(self.L.b200tfhe_register_lut(self.h, _ptr(acc), C.byref(i)))
+        return i.value
+
+    def register_lut_from_table(self, table):
+        t = np.ascontiguousarray(table, dtype=np.uint64)
+        i = C.c_uint32()
+        self._check(self.L.b200tfhe_register_lut_from_table(self.h, _ptr(t), t.size, C.byref(i)))
+        return i.value
+
+    def generate_lookup_table(self, f):
+        """ServerKey::generate_lookup_table (shortint/server_key/mod.rs:383-399) -> device LUT id."""
+        m = self.params.message_modulus * self.params.carry_modulus
+        return self.register_lut_from_table([f(x) for x in range(m)])
+
+    # ---- host-buffer hot path
+    def keyswitch_batch(self, cts):
+        cts = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1, self.params.big_lwe_size)
+        out = np.empty((cts.shape[0], self.params.small_lwe_size), dtype=np.uint64)
+        self._check(self.L.b200tfhe_keyswitch_batch(self.h, _ptr(cts), _ptr(out), cts.shape[0]))
+        return out
+
+    def pbs_batch(self, small_cts, lut_ids=None):
+        cts = np.ascontiguousarray(small_cts, dtype=np.uint64).reshape(-1, self.params.small_lwe_size)
+        ids = None if lut_ids is None else np.ascontiguousarray(lut_ids, dtype=np.uint32)
+        out = np.empty((cts.shape[0], self.params.big_lwe_size), dtype=np.uint64)
+        self._check(self.L.b200tfhe_pbs_batch(self.h, _ptr(cts), _ptr(ids), _ptr(out), cts.shape[0]))
+        return out
+
+    def ks_pbs_batch(self, cts, lut_ids=None, out=None):
+        """apply_lookup_table over a batch (host buffers; numpy arrays or pinned torch tensors)."""
+        if isinstance(cts, np.ndarray):
+            cts = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1, self.params.big_lwe_size)
+            batch = cts.shape[0]
+            if out is None:
+                out = np.empty((batch, self.params.big_lwe_size), dtype=np.uint64)
+        else:
+            batch = cts.shape[0]
+            assert out is not None
+        ids = lut_ids
+        if ids is not None and isinstance(ids, (list, tuple)):
+            ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._check(self.L.b200tfhe_ks_pbs_batch(self.h, _ptr(cts), _ptr(ids), _ptr(out), batch))
+        return out
+
+    # ---- device-buffer hot path (torch CUDA tensors or raw device addresses)
+    def keyswitch_batch_device(self, d_in, d_out, batch):
+        self._check(self.L.b200tfhe_keyswitch_batch_device(self.h, _ptr(d_in), _ptr(d_out), batch))
+
+    def pbs_batch_device(self, d_in, d_lut_ids, d_out, batch):
+        self._check(self.L.b200tfhe_pbs_batch_device(self.h, _ptr(d_in), _ptr(d_lut_ids), _ptr(d_out), batch))
+
+    def ks_pbs_batch_device(self, d_in, d_lut_ids, d_out, batch):
+        self._check(self.L.b200tfhe_ks_pbs_batch_device(self.h, _ptr(d_in), _ptr(d_lut_ids), _ptr(d_out), batch))
+
+    def lwe_linear_batch_device(self, d_x, d_y, d_ia, d_ib, d_ca, d_cb, d_pt, d_out, batch, lwe_size):
+        self._check(self.L.b200tfhe_lwe_linear_batch_device(
+            self.h, _ptr(d_x), _ptr(d_y), _ptr(d_ia), _ptr(d_ib), _ptr(d_ca), _ptr(d_cb), _ptr(d_pt),
+            _ptr(d_out), batch, lwe_size))
+
+    def sync(self):
+        self._check(self.L.b200tfhe_sync(self.h))
+
+    def stream(self):
+        s = C.c_void_p()
+        self._check(self.L.b200tfhe_stream(self.h, C.byref(s)))
+        return s.value
+
+    # ---- measurement
+    def set_profiling(self, on):
+        self._check(self.L.b200tfhe_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_times(self, reset=False):
+        a, b = C.c_double(), C.c_double()
+        na, nb = C.c_uint64(), C.c_uint64()
+        self._check(self.L.b200tfhe_get_kernel_times(self.h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb),
+                                                     1 if reset else 0))
+        return {"ks_ms": a.value, "ks_launches": na.value, "pbs_ms": b.value, "pbs_launches": nb.value}
+
+    def set_pbs_variant(self, v):
+        self._check(self.L.b200tfhe_set_pbs_variant(self.h, v))
+
+    def debug_negacyclic_mul(self, a_int, b_torus, out):
+        a = np.ascontiguousarray(a_int, dtype=np.uint64).reshape(-1, 2048)
+        b = np.ascontiguousarray(b_torus, dtype=np.uint64).reshape(-1, 2048)
+        assert out.dtype == np.uint64 and out.shape == a.shape and out.flags["C_CONTIGUOUS"]
+        self._check(self.L.b200tfhe_debug_negacyclic_mul(self.h, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        return out
