@@ -1,0 +1,47 @@
+"""CPU tests of the drop-in boundary: the library loads, exports every symbol include/b200tfhe.h
+declares, and fails loudly (no fallback) when no GPU is present."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "b200tfhe.h")).read()
+    return sorted(set(re.findall(r"\bint\s+(b200tfhe_\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    from tfhe_rs_string_b200 import engine
+    assert _header_symbols() == sorted(engine.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_symbol():
+    import tfhe_rs_string_b200 as T
+    if not os.path.exists(T.lib_path()):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(T.lib_path())
+    for name in _header_symbols():
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback():
+    import torch
+    import tfhe_rs_string_b200 as T
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(T.B200TfheError, match="no CPU fallback"):
+        T.Engine()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tfhe_rs_string_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower().replace("no oracle", ""), f

@@ -1,0 +1,167 @@
+"""GPU parity tests (run on a B200 with `-m gpu`): CUDA path through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+U64 = np.uint64
+PHASE_BOUND = 1 << 48   # |phase_gpu - phase_oracle| (expected ~2^43); delta/2 = 2^58
+
+
+def _negacyclic_exact(a, b):
+    n = len(a)
+    full = np.convolve(np.array(a, dtype=object), np.array(b, dtype=object))
+    res = full[:n].copy()
+    res[:n - 1] -= full[n:]
+    return np.array([int(x) % 2**64 for x in res], dtype=U64)
+
+
+def test_fft_product_vs_schoolbook(engine):
+    # reference tolerance, fft/tests.rs:82-222: 2^(64-(52-16-log2 N)) for 16-bit integer polys
+    rng = np.random.default_rng(5)
+    cnt = 4
+    a = rng.integers(-2**15, 2**15, (cnt, 2048))
+    b = rng.integers(0, 2**64, (cnt, 2048), dtype=U64)
+    out0 = rng.integers(0, 2**64, (cnt, 2048), dtype=U64)
+    out = out0.copy()
+    engine.debug_negacyclic_mul(a.astype(np.int64).view(U64), b, out)
+    for i in range(cnt):
+        ref = _negacyclic_exact(a[i], b[i]) + out0[i]
+        dist = np.abs((out[i] - ref).astype(np.int64)).max()
+        assert dist <= 2 ** (64 - (52 - 16 - 11)), dist
+    # PBS-sized digits (23 bit): still far below delta/2
+    a = rng.integers(-2**22, 2**22 + 1, (1, 2048))
+    out = np.zeros((1, 2048), dtype=U64)
+    engine.debug_negacyclic_mul(a.astype(np.int64).view(U64), b[:1], out)
+    dist = np.abs((out[0] - _negacyclic_exact(a[0], b[0])).astype(np.int64)).max()
+    assert dist <= 2 ** (64 - (52 - 23 - 11)), dist
+
+
+@pytest.mark.parametrize("batch", [1, 63, 64, 65, 300])
+def test_keyswitch_bit_exact(engine, real_keys, batch):
+    rng = np.random.default_rng(100 + batch)
+    cts = real_keys.encrypt_batch(rng.integers(0, 32, batch), seed=200 + batch)
+    got = engine.keyswitch_batch(cts)
+    ref = real_keys.keyswitch_batch(cts)
+    assert np.array_equal(got, ref)
+
+
+def test_keyswitch_adversarial_inputs(engine, real_keys):
+    # all-zero, all-ones, rounding boundaries of the KS decomposer (shift 48)
+    n = real_keys.params.big_lwe_size
+    rows = [np.zeros(n, dtype=U64), np.full(n, 2**64 - 1, dtype=U64), np.full(n, (1 << 48), dtype=U64),
+            np.full(n, (1 << 48) - 1, dtype=U64), np.full(n, 0x8000000000000000, dtype=U64),
+            np.full(n, 0x7FFF800000000000, dtype=U64)]
+    cts = np.stack(rows)
+    assert np.array_equal(engine.keyswitch_batch(cts), real_keys.keyswitch_batch(cts))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_pbs_parity(engine, real_keys, variant):
+    engine.set_pbs_variant(variant)
+    try:
+        msgs = np.arange(40) % 32          # includes padding-bit-set inputs (negacyclic branch)
+        cts = real_keys.encrypt_batch(msgs, seed=300)
+        small = real_keys.keyswitch_batch(cts)
+        luts = [real_keys.lut(lambda x: x), real_keys.lut(lambda x: (5 * x + 3) % 16)]
+        ids = [engine.register_lut(l) for l in luts]
+        idx = (np.arange(40) % 2).astype(np.uint32)
+        got = engine.pbs_batch(small, np.array([ids[i] for i in idx], dtype=np.uint32))
+        ref = real_keys.bootstrap_batch(small, np.stack(luts), idx)
+        # (1) decrypted values bit-exact
+        assert np.array_equal(real_keys.decrypt_batch(got), real_keys.decrypt_batch(ref))
+        f = [lambda x: x, lambda x: (5 * x + 3) % 16]
+        exp = [(f[i](m) if m < 16 else (32 - f[i](m - 16)) % 32) for m, i in zip(msgs, idx)]
+        assert list(real_keys.decrypt_batch(got)) == exp
+        # (2) phase difference vs oracle bounded (FFT rounding only)
+        dphase = (real_keys.phase_batch(got) - real_keys.phase_batch(ref)).astype(np.int64)
+        assert np.abs(dphase).max() < PHASE_BOUND, np.abs(dphase).max()
+    finally:
+        engine.set_pbs_variant(0)
+
+
+def test_ks_pbs_all_messages_full_batch(engine, real_keys):
+    # BASELINE config[0]: 1024 ciphertexts, identity LUT, messages i mod 16
+    B = 1024
+    msgs = np.arange(B) % 16
+    cts = real_keys.encrypt_batch(msgs, seed=0xC0FFEE)
+    lid = engine.generate_lookup_table(lambda x: x)
+    out = engine.ks_pbs_batch(cts, np.full(B, lid, dtype=np.uint32))
+    assert np.array_equal(real_keys.decrypt_batch(out), msgs.astype(U64))
+    # idempotence property: bootstrapping the output again gives the same messages
+    out2 = engine.ks_pbs_batch(out, np.full(B, lid, dtype=np.uint32))
+    assert np.array_equal(real_keys.decrypt_batch(out2), msgs.astype(U64))
+    # noise after PBS must be far below delta/2
+    ph = real_keys.phase_batch(out[:64])
+    err = (ph - (msgs[:64].astype(U64) * U64(real_keys.params.delta))).astype(np.int64)
+    assert np.abs(err).max() < (1 << 56)
+
+
+def test_ks_pbs_stress_max_noise(engine, real_keys):
+    # inputs at maximum legal noise level (5 fresh ciphertexts summed) and the
+    # bivariate pack 4*lhs + rhs (shortint/server_key/bivariate_pbs.rs:173-178)
+    rng = np.random.default_rng(7)
+    B = 256
+    parts = rng.integers(0, 4, (5, B))
+    parts[:, :] = np.minimum(parts, 3)
+    tot = parts.sum(axis=0)
+    keep = tot < 16
+    cts = sum(real_keys.encrypt_batch(parts[i], seed=400 + i) for i in range(5))
+    lid = engine.generate_lookup_table(lambda x: x)
+    out = engine.ks_pbs_batch(cts[keep], np.full(int(keep.sum()), lid, dtype=np.uint32))
+    assert np.array_equal(real_keys.decrypt_batch(out), tot[keep].astype(U64))
+    lhs, rhs = rng.integers(0, 4, B), rng.integers(0, 4, B)
+    packed = real_keys.encrypt_batch(lhs, seed=500) * U64(4) + real_keys.encrypt_batch(rhs, seed=501)
+    eq = engine.generate_lookup_table(lambda x: int((x // 4) % 4 == (x % 4) % 4))
+    out = engine.ks_pbs_batch(packed, np.full(B, eq, dtype=np.uint32))
+    assert np.array_equal(real_keys.decrypt_batch(out), (lhs == rhs).astype(U64))
+
+
+def test_lut_registry_and_errors(engine, real_keys):
+    import tfhe_rs_string_b200 as T
+    a = engine.register_lut(real_keys.lut(lambda x: x ^ 1))
+    b = engine.register_lut(real_keys.lut(lambda x: x ^ 1))
+    assert a == b
+    assert engine.generate_lookup_table(lambda x: x ^ 1) == a      # same table built on the library side
+    cts = real_keys.encrypt_batch(np.arange(4), seed=1)
+    with pytest.raises(T.B200TfheError):
+        engine.ks_pbs_batch(cts, np.array([10**6] * 4, dtype=np.uint32))
+    # empty batch is a no-op
+    out = engine.ks_pbs_batch(np.zeros((0, real_keys.params.big_lwe_size), dtype=U64), None)
+    assert out.shape[0] == 0
+    with pytest.raises(T.B200TfheError):
+        T.Engine(T.Params(742, 2, 1024, 23, 1, 3, 5, 4, 4))
+
+
+def test_lwe_linear_device(engine, real_keys):
+    import torch
+    rng = np.random.default_rng(9)
+    B, n = 50, real_keys.params.big_lwe_size
+    x = rng.integers(0, 2**64, (B, n), dtype=U64)
+    y = rng.integers(0, 2**64, (B, n), dtype=U64)
+    ia = rng.integers(0, B, B).astype(np.int32); ib = rng.integers(0, B, B).astype(np.int32)
+    ca = rng.integers(-4, 5, B).astype(np.int64); cb = rng.integers(-4, 5, B).astype(np.int64)
+    pt = rng.integers(0, 2**64, B, dtype=U64)
+    t = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == U64 else a).cuda()
+    dx, dy, dia, dib, dca, dcb, dpt = map(t, (x, y, ia, ib, ca, cb, pt))
+    dout = torch.empty((B, n), dtype=torch.int64, device="cuda")
+    engine.lwe_linear_batch_device(dx, dy, dia, dib, dca, dcb, dpt, dout, B, n)
+    engine.sync()
+    got = dout.cpu().numpy().view(U64)
+    ref = x[ia] * ca.astype(U64)[:, None] + y[ib] * cb.astype(U64)[:, None]
+    ref[:, -1] += pt
+    assert np.array_equal(got, ref)
+
+
+def test_device_entry_points_match_host(engine, real_keys):
+    import torch
+    B = 96
+    cts = real_keys.encrypt_batch(np.arange(B) % 16, seed=77)
+    lid = engine.generate_lookup_table(lambda x: (x + 1) % 16)
+    host = engine.ks_pbs_batch(cts, np.full(B, lid, dtype=np.uint32))
+    d_in = torch.from_numpy(cts.view(np.int64)).cuda()
+    d_ids = torch.full((B,), lid, dtype=torch.int32, device="cuda")
+    d_out = torch.empty_like(d_in)
+    torch.cuda.synchronize()
+    engine.ks_pbs_batch_device(d_in, d_ids, d_out, B)
+    engine.sync()
+    assert np.array_equal(d_out.cpu().numpy().view(U64), host)   # same kernels, same order: deterministic
