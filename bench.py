@@ -1,0 +1,317 @@
+#!/usr/bin/env python3
+"""bench.py -- KS+PBS throughput of libb200tfhe (PARAM_MESSAGE_2_CARRY_2_KS_PBS) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                     (CPU arm: the oracle port on host cores)
+
+A step = one pass of the hot path (batched keyswitch + programmable bootstrap through the C ABI)
+over one batch of `--batch` radix blocks per GPU (default 4096 = the block count of BASELINE.json
+configs[1]; weak scaling: every rank processes its own batch, no data-path collective, the server
+key is broadcast once over NCCL before the timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PBS = 262144 * 742          # BASELINE.md section 2 / SURVEY 8d: algorithmic FP64 flop per PBS
+BSK_BYTES = 742 * 4 * 1024 * 16      # Fourier BSK streamed once per resident wave of ciphertexts
+KSK_BYTES = 2048 * 5 * 743 * 8
+METRIC = "KS+PBS/sec (PARAM_MESSAGE_2_CARRY_2)"
+UNIT = "KS+PBS/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="ciphertexts (radix blocks) per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="ciphertexts in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="PBS kernel variant (b200tfhe_set_pbs_variant)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measure_fp64_peak():
+    """Measured FP64 FMA peak of this GPU (MEASURED_PEAKS.json carries HBM and bf16 only)."""
+    exe = os.path.join(ROOT, "tfhe_rs_string_b200", "microbench")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        best = 0.0
+        for line in out.splitlines():
+            try:
+                d = json.loads(line)
+            except Exception:
+                continue
+            if d.get("bench") == "dfma":
+                best = max(best, d["tflops"])
+        if best > 0:
+            return best, "measured live: tfhe_rs_string_b200/microbench dfma (8 FMA chains/thread, 32 warps/SM)"
+    except Exception:
+        pass
+    return 34.07, "fallback: microbench dfma measured on this pool's B200 (profiles/r01_microbench.jsonl)"
+
+
+def cpu_baseline(sample, threads):
+    """The oracle port (oracle/tfhe_oracle.cpp: same algorithm as the reference's CPU path, one
+    ciphertext per thread like benches/core_crypto/pbs_bench.rs:517-531) on the host cores."""
+    import numpy as np
+    from oracle import oracle as O
+    p = O.params_message_2_carry_2()
+    keys = O.Keyset(p, seed=0xB200, n_threads=threads)
+    cts = keys.encrypt_batch(np.arange(sample) % 16, seed=0xC0FFEE)
+    lut = keys.lut(lambda x: x)
+    keys.ks_pbs_batch(cts[:threads], lut, n_threads=threads)          # warm caches / page in keys
+    t0 = time.perf_counter()
+    out = keys.ks_pbs_batch(cts, lut, n_threads=threads)
+    dt = time.perf_counter() - t0
+    ok = bool((keys.decrypt_batch(out) == (np.arange(sample) % 16)).all())
+    return sample / dt, dt, ok
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample or max(32, min(256, 2 * threads))
+    import numpy as np
+    from oracle import oracle as O
+    p = O.params_message_2_carry_2()
+    keys = O.Keyset(p, seed=0xB200, n_threads=threads)
+    cts = keys.encrypt_batch(np.arange(sample) % 16, seed=0xC0FFEE)
+    lut = keys.lut(lambda x: x)
+    for _ in range(max(1, min(args.warmup, 1))):
+        keys.ks_pbs_batch(cts[:threads], lut, n_threads=threads)
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        keys.ks_pbs_batch(cts, lut, n_threads=threads)
+    dt = (time.perf_counter() - t0) / steps
+    v = sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64+u64", "data": "synthetic",
+        "config": {"workload": f"shortint KS+PBS (apply_lookup_table), PARAM_MESSAGE_2_CARRY_2_KS_PBS, bounded sample of "
+                               f"{sample} ciphertexts per step of the {args.batch}-block batch, CPU"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} ciphertexts x {steps} steps, one ciphertext per thread (oracle/tfhe_oracle.cpp; "
+                                   "the Rust reference cannot be built here: no cargo, concrete-fft un-vendored)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import tfhe_rs_string_b200 as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    B = args.batch
+    p = T.Params.message_2_carry_2()
+    eng = T.Engine(p, device=local)
+    eng.set_pbs_variant(args.variant)
+
+    # ---- server key: rank 0 uploads (H2D + std->Fourier on the GPU), then ONE NCCL broadcast
+    t_key0 = time.perf_counter()
+    if rank == 0:
+        rng = np.random.default_rng(0xB200)
+        eng.load_ksk(rng.integers(0, 2**64, 2048 * 5 * 743, dtype=np.uint64))
+        eng.load_bsk_standard(rng.integers(0, 2**64, 742 * 4 * 2048, dtype=np.uint64))
+    if world > 1:
+        ptr, nbytes = eng.key_arena()
+
+        class _Arena:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        arena = torch.as_tensor(_Arena(), device=f"cuda:{local}")
+        dist.broadcast(arena, src=0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            eng.keys_adopt()
+    key_setup_s = time.perf_counter() - t_key0
+
+    # ---- synthetic inputs of the named shape (uniform u64 LWE words are what ciphertexts look like)
+    rng = np.random.default_rng(0xC0FFEE + rank)
+    lut_eq = eng.generate_lookup_table(lambda x: int((x // 4) % 4 == x % 4))      # radix block equality
+    lut_id = eng.generate_lookup_table(lambda x: x)
+    h_in = [torch.from_numpy(rng.integers(-2**63, 2**63, (B, p.big_lwe_size), dtype=np.int64)).pin_memory() for _ in range(2)]
+    h_ids = torch.from_numpy(np.where(np.arange(B) % 5 == 4, lut_id, lut_eq).astype(np.int32)).pin_memory()
+    h_out = torch.empty((B, p.big_lwe_size), dtype=torch.int64).pin_memory()
+    d_in = [h.cuda() for h in h_in]
+    d_ids = h_ids.cuda()
+    d_out = torch.empty((B, p.big_lwe_size), dtype=torch.int64, device="cuda")
+    stream = torch.cuda.ExternalStream(eng.stream(), device=f"cuda:{local}")
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        eng.ks_pbs_batch_device(d_in[i & 1], d_ids, d_out, B)
+
+    def step_e2e(i):
+        eng.ks_pbs_batch(h_in[i & 1], h_ids, out=h_out)      # H2D + KS + PBS + D2H, synchronous
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        eng.sync()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step_fn(i)
+        e1.record(stream)
+        eng.sync()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput (inputs already in HBM), clocks sampled during the region
+    eng.set_profiling(True)
+    sampler = ClockSampler(local)
+    for i in range(args.warmup):
+        step_device(i)
+    eng.sync()
+    eng.kernel_times(reset=True)
+    sampler.start()
+    ms = timed(step_device, args.steps, 0)
+    clocks = sampler.stop()
+    kt = eng.kernel_times(reset=True)
+    eng.set_profiling(False)
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI call (pinned host memory, copies inside the region)
+    e2e_steps = max(3, args.steps // 2)
+    ms_e2e = timed(step_e2e, e2e_steps, 2)
+    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        pbs_ms = kt["pbs_ms"] / max(1, kt["pbs_launches"])
+        ks_ms = kt["ks_ms"] / max(1, kt["ks_launches"])
+        peak, peak_src = measure_fp64_peak()
+        achieved = B * FLOP_PER_PBS / (pbs_ms * 1e-3) / 1e12
+        n_waves = -(-B // (148 * 4))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64+u64", "data": "synthetic",
+            "config": {
+                "workload": f"shortint KS+PBS (apply_lookup_table batch), PARAM_MESSAGE_2_CARRY_2_KS_PBS, {B} radix blocks per GPU "
+                            "per step (block count of configs[1]: 1024 FheUint8 pairs x 4 blocks), bivariate block-eq LUT x4 + identity LUT x1",
+                "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"independent ciphertext shards x{world}, key broadcast once (NCCL)",
+                "l2": "working set per step (in 67 MB + out 67 MB + KS out 24 MB + keys 110 MB) exceeds the 126 MB L2; two alternating input buffers",
+                "pbs_variant": args.variant, "key_setup_s": key_setup_s,
+            },
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "pbs_kernel", "kernel_ms": pbs_ms, "ks_kernel_ms": ks_ms,
+                "kernel_share_of_step": pbs_ms / ms_per_step, "peak_source": peak_src,
+                "algorithmic_flop_per_unit": FLOP_PER_PBS,
+                "bsk_stream_GBps": n_waves * BSK_BYTES / (pbs_ms * 1e-3) / 1e9,
+                "hbm_peak_GBps_measured": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * p.big_lwe_size * 8 + B * 4),
+                    "d2h_bytes_per_step": int(B * p.big_lwe_size * 8), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(kt["pbs_launches"] + kt["ks_launches"]),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            sample = args.cpu_sample or max(32, min(256, 2 * threads))
+            v, dt, ok = cpu_baseline(sample, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{sample} of the {B} ciphertexts, identity LUT, {dt:.1f} s, decrypt ok={ok}"}
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

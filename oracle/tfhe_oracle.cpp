@@ -128,64 +128,89 @@ const FftPlan &get_plan(uint32_t N) {
     return ref;
 }
 
-/* in-place radix-2 DIT on split re/im arrays; conj_tw selects the inverse transform */
-void fft_core(const FftPlan &pl, double *re, double *im, bool inverse) {
+/* Forward transform: radix-2 decimation in frequency, natural order in, bit-reversed order out.
+ * Inverse: radix-2 decimation in time with conjugated twiddles, bit-reversed in, natural out.
+ * The Fourier-domain ordering is therefore bit-reversed; that is free (see file header): every
+ * Fourier-domain operation on this path is pointwise. */
+static inline size_t stage_off(uint32_t len) { return (size_t)len / 2 - 1; }
+
+void fft_forward(const FftPlan &pl, double *__restrict re, double *__restrict im) {
     const uint32_t n = pl.n;
-    for (uint32_t i = 0; i < n; i++) {
-        uint32_t j = pl.brev[i];
-        if (j > i) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
-    }
-    size_t off = 0;
-    const double sgn = inverse ? -1.0 : 1.0;
-    for (uint32_t len = 2; len <= n; len <<= 1) {
+    for (uint32_t len = n; len >= 2; len >>= 1) {
         const uint32_t half = len / 2;
-        const double *wr = &pl.st_re[off], *wi = &pl.st_im[off];
+        const double *__restrict wr = &pl.st_re[stage_off(len)], *__restrict wi = &pl.st_im[stage_off(len)];
         for (uint32_t base = 0; base < n; base += len) {
-            double *ar = re + base, *ai = im + base, *br = re + base + half, *bi = im + base + half;
+            double *__restrict ar = re + base, *__restrict ai = im + base;
+            double *__restrict br = re + base + half, *__restrict bi = im + base + half;
             for (uint32_t t = 0; t < half; t++) {
-                double wre = wr[t], wim = sgn * wi[t];
-                double xr = br[t] * wre - bi[t] * wim;
-                double xi = br[t] * wim + bi[t] * wre;
-                br[t] = ar[t] - xr; bi[t] = ai[t] - xi;
-                ar[t] = ar[t] + xr; ai[t] = ai[t] + xi;
+                const double dr = ar[t] - br[t], di = ai[t] - bi[t];
+                ar[t] += br[t]; ai[t] += bi[t];
+                br[t] = dr * wr[t] - di * wi[t];
+                bi[t] = dr * wi[t] + di * wr[t];
             }
         }
-        off += half;
     }
 }
+
+void fft_inverse(const FftPlan &pl, double *__restrict re, double *__restrict im) {
+    const uint32_t n = pl.n;
+    for (uint32_t len = 2; len <= n; len <<= 1) {
+        const uint32_t half = len / 2;
+        const double *__restrict wr = &pl.st_re[stage_off(len)], *__restrict wi = &pl.st_im[stage_off(len)];
+        for (uint32_t base = 0; base < n; base += len) {
+            double *__restrict ar = re + base, *__restrict ai = im + base;
+            double *__restrict br = re + base + half, *__restrict bi = im + base + half;
+            for (uint32_t t = 0; t < half; t++) {
+                const double xr = br[t] * wr[t] + bi[t] * wi[t];   /* b * conj(w) */
+                const double xi = bi[t] * wr[t] - br[t] * wi[t];
+                br[t] = ar[t] - xr; bi[t] = ai[t] - xi;
+                ar[t] += xr; ai[t] += xi;
+            }
+        }
+    }
+}
+
+struct FftScratch {
+    std::vector<double> re, im;
+    void ensure(uint32_t n) { if (re.size() < n) { re.resize(n); im.resize(n); } }
+};
+static thread_local FftScratch tl_fft;
 
 /* fft/mod.rs:220-239 + 496-515: z_j = (i64(p_j) + i*i64(p_{j+N/2})) * w_j, then forward DFT */
 void forward_integer(const FftPlan &pl, double *out /*interleaved*/, const uint64_t *poly) {
     const uint32_t n = pl.n;
-    std::vector<double> re(n), im(n);
+    tl_fft.ensure(n);
+    double *re = tl_fft.re.data(), *im = tl_fft.im.data();
     for (uint32_t j = 0; j < n; j++) {
         double a = (double)(int64_t)poly[j], b = (double)(int64_t)poly[j + n];
         re[j] = a * pl.tw_re[j] - b * pl.tw_im[j];
         im[j] = a * pl.tw_im[j] + b * pl.tw_re[j];
     }
-    fft_core(pl, re.data(), im.data(), false);
+    fft_forward(pl, re, im);
     for (uint32_t j = 0; j < n; j++) { out[2 * j] = re[j]; out[2 * j + 1] = im[j]; }
 }
 
 /* fft/mod.rs:197-218: same with inputs scaled by 2^-64 (key conversion) */
 void forward_torus(const FftPlan &pl, double *out, const uint64_t *poly) {
     const uint32_t n = pl.n;
-    std::vector<double> re(n), im(n);
+    tl_fft.ensure(n);
+    double *re = tl_fft.re.data(), *im = tl_fft.im.data();
     for (uint32_t j = 0; j < n; j++) {
         double a = (double)(int64_t)poly[j] * 0x1p-64, b = (double)(int64_t)poly[j + n] * 0x1p-64;
         re[j] = a * pl.tw_re[j] - b * pl.tw_im[j];
         im[j] = a * pl.tw_im[j] + b * pl.tw_re[j];
     }
-    fft_core(pl, re.data(), im.data(), false);
+    fft_forward(pl, re, im);
     for (uint32_t j = 0; j < n; j++) { out[2 * j] = re[j]; out[2 * j + 1] = im[j]; }
 }
 
 /* fft/mod.rs:285-304 + 539-557: inverse DFT, times conj(w_j)/n, from_torus, wrapping add */
 void add_backward_torus(const FftPlan &pl, uint64_t *poly, const double *fourier) {
     const uint32_t n = pl.n;
-    std::vector<double> re(n), im(n);
+    tl_fft.ensure(n);
+    double *re = tl_fft.re.data(), *im = tl_fft.im.data();
     for (uint32_t j = 0; j < n; j++) { re[j] = fourier[2 * j]; im[j] = fourier[2 * j + 1]; }
-    fft_core(pl, re.data(), im.data(), true);
+    fft_inverse(pl, re, im);
     const double norm = 1.0 / (double)n;
     for (uint32_t j = 0; j < n; j++) {
         double wr = pl.tw_re[j] * norm, wi = -pl.tw_im[j] * norm;

@@ -4,7 +4,15 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 U64 = np.uint64
-PHASE_BOUND = 1 << 48   # |phase_gpu - phase_oracle| (expected ~2^43); delta/2 = 2^58
+# Post-PBS phase difference between two correct implementations.  SURVEY 8c proposed 2^48 from
+# FFT rounding alone, but that ignores the decomposer: a 2^39-sized rounding difference in the
+# accumulator flips the 2^41-rounded digit of ~25% of the coefficients at every CMUX step, which
+# re-draws the decomposition-noise term (2^41 * sqrt(#flips * key weight) ~ 2^45 per step, ~2^50
+# over 742 steps) -- the same order as the PBS output noise itself (std ~2^48).  Any two FFT
+# implementations (the reference's own AVX2 vs AVX-512 builds included) differ by that much.  The
+# stated bound is 2^53 = delta/64 (delta/2 = 2^58 is the decryption margin), plus a statistical
+# check that the GPU's output noise has the same spread as the oracle's.
+PHASE_BOUND = 1 << 53
 
 
 def _negacyclic_exact(a, b):
@@ -75,6 +83,12 @@ def test_pbs_parity(engine, real_keys, variant):
         # (2) phase difference vs oracle bounded (FFT rounding only)
         dphase = (real_keys.phase_batch(got) - real_keys.phase_batch(ref)).astype(np.int64)
         assert np.abs(dphase).max() < PHASE_BOUND, np.abs(dphase).max()
+        # (3) same noise spread: error vs the ideal phase f(m)*delta, GPU vs oracle
+        ideal = np.array(exp, dtype=U64) * U64(real_keys.params.delta)
+        e_gpu = (real_keys.phase_batch(got) - ideal).astype(np.int64).astype(np.float64)
+        e_ref = (real_keys.phase_batch(ref) - ideal).astype(np.int64).astype(np.float64)
+        assert 0.6 < e_gpu.std() / e_ref.std() < 1.6, (e_gpu.std(), e_ref.std())
+        assert np.abs(e_gpu).max() < (1 << 54)
     finally:
         engine.set_pbs_variant(0)
 
