@@ -79,7 +79,8 @@ int b200tfhe_keys_adopt(b200tfhe_ctx *ctx);
  * fill_accumulator, shortint/server_key/mod.rs:383-399, shortint/engine/mod.rs:72-128) and
  * returns its id.  Content-addressed: registering the same table twice returns the same id. */
 int b200tfhe_register_lut(b200tfhe_ctx *ctx, const uint64_t *glwe_acc, uint32_t *id);
-/* Device-side fill_accumulator for a function table f(0..message_modulus*carry_modulus-1). */
+/* fill_accumulator (shortint/engine/mod.rs:72-128) for a function table f(0..message_modulus*carry_modulus-1),
+ * then register_lut: what ServerKey::generate_lookup_table does, with the table kept on the device. */
 int b200tfhe_register_lut_from_table(b200tfhe_ctx *ctx, const uint64_t *table, size_t table_len, uint32_t *id);
 
 /* ---- hot path, host buffers ----------------------------------------------------------- */
@@ -119,8 +120,9 @@ int b200tfhe_set_profiling(b200tfhe_ctx *ctx, int enabled);
 /* Accumulated device time (ms) and launch counts since the last reset; synchronises. */
 int b200tfhe_get_kernel_times(b200tfhe_ctx *ctx, double *ks_ms, uint64_t *ks_launches, double *pbs_ms,
                               uint64_t *pbs_launches, int reset);
-/* Selects the PBS kernel variant: 0 = default (TMEM accumulator, 4 ciphertexts/CTA),
- * 1 = shared-memory accumulator (2/CTA), 2 = TMEM, 6 ciphertexts/CTA. */
+/* Selects the PBS kernel variant (all keep the accumulator in TMEM): 0 = default, 4 ciphertexts
+ * per CTA, BSK slice staged once per CTA in shared memory by a bulk async copy; 1 = 4 per CTA,
+ * BSK read from L2 by every warp; 2 = 6 per CTA, BSK read from L2. */
 int b200tfhe_set_pbs_variant(b200tfhe_ctx *ctx, int variant);
 
 /* ---- unit-test hooks (exercise exactly the transforms the PBS kernel uses) ------------ */

@@ -177,16 +177,16 @@ int launch_ks(b200tfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, size_t b
     return 0;
 }
 
-template <int CTS, bool TMEM>
+template <int CTS, bool BSK_SMEM>
 int launch_pbs_variant(b200tfhe_ctx *ctx, const PbsArgs &a) {
     static bool configured[16] = {};
-    constexpr size_t smem = pbs_smem_bytes<CTS, TMEM>();
+    constexpr size_t smem = pbs_smem_bytes<CTS, BSK_SMEM>();
     if (!configured[ctx->device & 15]) {
-        CU_TRY(ctx, cudaFuncSetAttribute(pbs_kernel<CTS, TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(ctx, cudaFuncSetAttribute(pbs_kernel<CTS, BSK_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[ctx->device & 15] = true;
     }
     const unsigned grid = (unsigned)((a.batch + CTS - 1) / CTS);
-    pbs_kernel<CTS, TMEM><<<grid, CTS * 64, smem, ctx->stream>>>(a);
+    pbs_kernel<CTS, BSK_SMEM><<<grid, CTS * 64, smem, ctx->stream>>>(a);
     return 0;
 }
 
@@ -199,8 +199,8 @@ int launch_pbs(b200tfhe_ctx *ctx, const uint64_t *d_small, const uint32_t *d_lut
     prof_begin(ctx, ctx->ev_pbs);
     int rc;
     switch (ctx->pbs_variant) {
-        case 1: rc = launch_pbs_variant<2, false>(ctx, a); break;
-        case 2: rc = launch_pbs_variant<6, true>(ctx, a); break;
+        case 1: rc = launch_pbs_variant<4, false>(ctx, a); break;
+        case 2: rc = launch_pbs_variant<6, false>(ctx, a); break;
         default: rc = launch_pbs_variant<4, true>(ctx, a); break;
     }
     prof_end(ctx, ctx->ev_pbs);

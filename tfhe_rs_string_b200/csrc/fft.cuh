@@ -76,18 +76,65 @@ __device__ __forceinline__ void fft32_dit(double (&xr)[32], double (&xi)[32]) {
     }
 }
 
+// Twiddle sources: T'[k1][lane] for k1 = 4*chunk .. 4*chunk+3, as 16 32-bit words
+// (re.lo, re.hi, im.lo, im.hi per twiddle).  issue() may be asynchronous; wait() completes it.
+struct GlobalTwiddles {   // plain global-memory table (key conversion / unit-test kernels)
+    const double2 *twid;
+    int lane;
+    __device__ __forceinline__ void issue(const int chunk, uint32_t (&r)[16]) const {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const double2 t = __ldg(twid + (chunk * 4 + kk) * 32 + lane);
+            r[4 * kk] = (uint32_t)__double2loint(t.x); r[4 * kk + 1] = (uint32_t)__double2hiint(t.x);
+            r[4 * kk + 2] = (uint32_t)__double2loint(t.y); r[4 * kk + 3] = (uint32_t)__double2hiint(t.y);
+        }
+    }
+    __device__ __forceinline__ void wait() const {}
+};
+
+// y = x * t  (CONJ: x * conj(t)) with t packed as 4 words at r[4*kk..]
+template <bool CONJ>
+__device__ __forceinline__ void cmul_tw(double &yr, double &yi, const double xr, const double xi,
+                                        const uint32_t (&r)[16], const int kk) {
+    const double tr = __hiloint2double((int)r[4 * kk + 1], (int)r[4 * kk]);
+    const double ti = __hiloint2double((int)r[4 * kk + 3], (int)r[4 * kk + 2]);
+    if (!CONJ) {
+        yr = fma(-xi, ti, xr * tr);
+        yi = fma(xi, tr, xr * ti);
+    } else {
+        yr = fma(xi, ti, xr * tr);
+        yi = fma(xi, tr, -(xr * ti));
+    }
+}
+
 // Forward transform.  In: x[brev5(m)] = twisted-by-C_m folded point l + 32*m (A_l NOT applied).
 // Out: x[k2] = F[lane + 32*k2].  tbuf: this warp's private 32x33 double2 buffer.
-__device__ __forceinline__ void fwd1024(double (&xr)[32], double (&xi)[32], double2 *tbuf,
-                                        const double2 *__restrict__ twid, const int lane) {
+template <class TW>
+__device__ __forceinline__ void fwd1024(double (&xr)[32], double (&xi)[32], double2 *tbuf, const TW &tw,
+                                        const int lane) {
+    uint32_t t0[16], t1[16];
     fft32_dit<false>(xr, xi);
+    tw.issue(0, t0);
 #pragma unroll
-    for (int k1 = 0; k1 < 32; k1++) {
-        const double2 t = twid[k1 * 32 + lane];
-        double2 y;
-        y.x = fma(-xi[k1], t.y, xr[k1] * t.x);
-        y.y = fma(xi[k1], t.x, xr[k1] * t.y);
-        tbuf[lane * kTStride + k1] = y;
+    for (int c2 = 0; c2 < 4; c2++) {
+        tw.wait();
+        tw.issue(2 * c2 + 1, t1);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int k1 = 8 * c2 + kk;
+            double2 y;
+            cmul_tw<false>(y.x, y.y, xr[k1], xi[k1], t0, kk);
+            tbuf[lane * kTStride + k1] = y;
+        }
+        tw.wait();
+        if (c2 < 3) tw.issue(2 * c2 + 2, t0);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int k1 = 8 * c2 + 4 + kk;
+            double2 y;
+            cmul_tw<false>(y.x, y.y, xr[k1], xi[k1], t1, kk);
+            tbuf[lane * kTStride + k1] = y;
+        }
     }
     __syncwarp();
 #pragma unroll
@@ -102,18 +149,33 @@ __device__ __forceinline__ void fwd1024(double (&xr)[32], double (&xi)[32], doub
 // Inverse transform (unnormalised; the 1/1024 is folded into the Fourier BSK).
 // In: x[brev5(k2)] = G[lane + 32*k2].  Out: x[m] = conj(A_l)-untwisted point l + 32*m; the caller
 // still has to multiply by conj(C_m).
-__device__ __forceinline__ void inv1024(double (&xr)[32], double (&xi)[32], double2 *tbuf,
-                                        const double2 *__restrict__ twid, const int lane) {
+template <class TW>
+__device__ __forceinline__ void inv1024(double (&xr)[32], double (&xi)[32], double2 *tbuf, const TW &tw,
+                                        const int lane) {
+    uint32_t t0[16], t1[16];
     fft32_dit<true>(xr, xi);
+    tw.issue(0, t0);
 #pragma unroll
     for (int l = 0; l < 32; l++) tbuf[lane * kTStride + l] = make_double2(xr[l], xi[l]);
     __syncwarp();
 #pragma unroll
-    for (int k1 = 0; k1 < 32; k1++) {
-        const double2 v = tbuf[k1 * kTStride + lane];
-        const double2 t = twid[k1 * 32 + lane];   // multiply by conj(t)
-        xr[brev5(k1)] = fma(v.y, t.y, v.x * t.x);
-        xi[brev5(k1)] = fma(v.y, t.x, -(v.x * t.y));
+    for (int c2 = 0; c2 < 4; c2++) {
+        tw.wait();
+        tw.issue(2 * c2 + 1, t1);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int k1 = 8 * c2 + kk;
+            const double2 v = tbuf[k1 * kTStride + lane];
+            cmul_tw<true>(xr[brev5(k1)], xi[brev5(k1)], v.x, v.y, t0, kk);
+        }
+        tw.wait();
+        if (c2 < 3) tw.issue(2 * c2 + 2, t0);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int k1 = 8 * c2 + 4 + kk;
+            const double2 v = tbuf[k1 * kTStride + lane];
+            cmul_tw<true>(xr[brev5(k1)], xi[brev5(k1)], v.x, v.y, t1, kk);
+        }
     }
     __syncwarp();
     fft32_dit<true>(xr, xi);

@@ -44,7 +44,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kKsThreads, 2) ks_kernel(const KsArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int kc = kKsIC * a.level;
     uint64_t *ktile = reinterpret_cast<uint64_t *>(smem);                           // [2][kc][BN]
     uint8_t *dtile = smem + (size_t)2 * kc * kKsBN * sizeof(uint64_t);               // [2][kc][BM]
@@ -55,11 +55,14 @@ __global__ void __launch_bounds__(kKsThreads, 2) ks_kernel(const KsArgs a) {
     const uint32_t half_b = 1u << (a.base_log - 1);
     const int rep_bits = a.base_log * a.level;
 
-    uint64_t acc[8][4];
+    // acc = alo + (ahi << 32): low words accumulate in 64 bits (32x32+64 IMAD.WIDE, < 2^49 over the
+    // whole sum), high words only matter mod 2^32 (one 32-bit IMAD); no carry chain per MAC.
+    uint64_t alo[8][4];
+    uint32_t ahi[8][4];
 #pragma unroll
     for (int c = 0; c < 8; c++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[c][j] = 0;
+        for (int j = 0; j < 4; j++) { alo[c][j] = 0; ahi[c][j] = 0; }
 
     auto stage_load = [&](int chunk, int buf) {
         // KSK rows [chunk*IC*L, +kc) x columns [col0, +BN)
@@ -119,13 +122,18 @@ __global__ void __launch_bounds__(kKsThreads, 2) ks_kernel(const KsArgs a) {
             const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(kt + (size_t)k * kKsBN);
             const ulonglong2 k23 = *reinterpret_cast<const ulonglong2 *>(kt + (size_t)k * kKsBN + 2);
             const uint2 dd = *reinterpret_cast<const uint2 *>(dt + (size_t)k * kKsBM);
-            const uint64_t kv[4] = {k01.x, k01.y, k23.x, k23.y};
+            const uint32_t klo[4] = {(uint32_t)k01.x, (uint32_t)k01.y, (uint32_t)k23.x, (uint32_t)k23.y};
+            const uint32_t khi[4] = {(uint32_t)(k01.x >> 32), (uint32_t)(k01.y >> 32), (uint32_t)(k23.x >> 32),
+                                     (uint32_t)(k23.y >> 32)};
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const uint32_t w = (c < 4) ? dd.x : dd.y;
-                const uint64_t d = (w >> (8 * (c & 3))) & 0xFFu;
+                const uint32_t d = (w >> (8 * (c & 3))) & 0xFFu;
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[c][j] += kv[j] * d;
+                for (int j = 0; j < 4; j++) {
+                    alo[c][j] += (uint64_t)klo[j] * d;
+                    ahi[c][j] += khi[j] * d;
+                }
             }
         }
         __syncthreads();
@@ -140,7 +148,7 @@ __global__ void __launch_bounds__(kKsThreads, 2) ks_kernel(const KsArgs a) {
             const int col = col0 + tx * 4 + j;
             if (col >= a.out_size) continue;
             // acc = sum (digit + B/2) * KSK  =>  -sum digit * KSK = colsum - acc
-            uint64_t v = a.colsum[col] - acc[c][j];
+            uint64_t v = a.colsum[col] - (alo[c][j] + ((uint64_t)ahi[c][j] << 32));
             if (col == a.out_size - 1) v += a.in[(size_t)ct * (a.n_in + 1) + a.n_in];
             a.out[(size_t)ct * a.out_size + col] = v;
         }
