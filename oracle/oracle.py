@@ -107,6 +107,10 @@ def lib():
         "orc_decrypt_small_phase": (C.c_uint64, [KS, _u64p]),
         "orc_decrypt_message_and_carry": (C.c_uint64, [KS, _u64p]),
         "orc_decrypt_batch": (None, [KS, _u64p, C.c_size_t, _u64p]),
+        "orc_circuit_last_error": (C.c_char_p, []),
+        "orc_circuit_info": (C.c_int, [C.c_char_p, _u64p, C.c_size_t, C.c_uint32, C.c_uint32, _u64p]),
+        "orc_circuit_run_cleartext": (C.c_int, [C.c_char_p, _u64p, C.c_size_t, C.c_uint32, C.c_uint32, _u64p, _u64p]),
+        "orc_circuit_run_encrypted": (C.c_int, [KS, C.c_char_p, _u64p, C.c_size_t, _u64p, _u64p, C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -209,3 +213,41 @@ class Keyset:
         out = np.zeros((B, self.params.big_lwe_size), dtype=np.uint64)
         self.L.orc_ks_pbs_batch(self.h, cts, luts, idx, out, B, n_threads or os.cpu_count() or 1)
         return out
+
+
+# ---- leveled circuits (host logic of the product, executed on the CPU for tests) -----------------
+def _shape(shape):
+    return np.ascontiguousarray(shape, dtype=np.uint64)
+
+
+def circuit_info(op, shape, message_modulus=4, carry_modulus=4):
+    info = np.zeros(6, dtype=np.uint64)
+    sh = _shape(shape)
+    if lib().orc_circuit_info(op.encode(), sh, len(sh), message_modulus, carry_modulus, info):
+        raise RuntimeError(lib().orc_circuit_last_error().decode())
+    return dict(zip(["n_inputs", "n_outputs", "n_pbs", "depth", "n_stages", "n_luts"], (int(x) for x in info)))
+
+
+def circuit_run_cleartext(op, shape, in_msgs, message_modulus=4, carry_modulus=4):
+    """Runs a named program (tfhe_rs_string_b200/csrc/programs.hpp) on clear message values."""
+    info = circuit_info(op, shape, message_modulus, carry_modulus)
+    m = np.ascontiguousarray(in_msgs, dtype=np.uint64).ravel()
+    assert m.size == info["n_inputs"], (m.size, info)
+    out = np.zeros(info["n_outputs"], dtype=np.uint64)
+    sh = _shape(shape)
+    if lib().orc_circuit_run_cleartext(op.encode(), sh, len(sh), message_modulus, carry_modulus, m, out):
+        raise RuntimeError(lib().orc_circuit_last_error().decode())
+    return out
+
+
+def circuit_run_encrypted(keys, op, shape, in_cts, n_threads=None):
+    """Same program on ciphertexts with the CPU oracle's KS+PBS (use toy parameters for speed)."""
+    p = keys.params
+    info = circuit_info(op, shape, p.message_modulus, p.carry_modulus)
+    cts = np.ascontiguousarray(in_cts, dtype=np.uint64).reshape(-1, p.big_lwe_size)
+    assert cts.shape[0] == info["n_inputs"]
+    out = np.zeros((info["n_outputs"], p.big_lwe_size), dtype=np.uint64)
+    sh = _shape(shape)
+    if lib().orc_circuit_run_encrypted(keys.h, op.encode(), sh, len(sh), cts, out, n_threads or os.cpu_count() or 1):
+        raise RuntimeError(lib().orc_circuit_last_error().decode())
+    return out

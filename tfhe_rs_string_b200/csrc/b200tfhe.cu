@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -170,7 +171,14 @@ int launch_ks(b200tfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, size_t b
     a.out_size = (int)ctx->small_size(); a.base_log = (int)ctx->p.ks_base_log; a.level = (int)ctx->p.ks_level;
     dim3 grid((a.out_size + kKsBN - 1) / kKsBN, (unsigned)((batch + kKsBM - 1) / kKsBM));
     prof_begin(ctx, ctx->ev_ks);
-    ks_kernel<<<grid, kKsThreads, ks_smem_bytes(a.level), ctx->stream>>>(a);
+    static const int dev_variant = getenv("B200TFHE_KS_VARIANT") ? atoi(getenv("B200TFHE_KS_VARIANT")) : 0;  // development knob
+    const size_t smem = ks_smem_bytes(a.level);
+    switch (dev_variant) {
+        case 1: ks_kernel<4, 2><<<grid, kKsThreads, smem, ctx->stream>>>(a); break;
+        case 2: ks_kernel<4, 1><<<grid, kKsThreads, smem, ctx->stream>>>(a); break;
+        case 3: ks_kernel<1, 1><<<grid, kKsThreads, smem, ctx->stream>>>(a); break;
+        default: ks_kernel<2, 1><<<grid, kKsThreads, smem, ctx->stream>>>(a); break;
+    }
     prof_end(ctx, ctx->ev_ks);
     CU_TRY(ctx, cudaGetLastError());
     ctx->ks_launches++;
@@ -281,8 +289,14 @@ int b200tfhe_ctx_create(const b200tfhe_params *params, int device, b200tfhe_ctx 
     if (cudaMalloc(&ctx->d_twid, tw.size() * sizeof(double2)) != cudaSuccess) return bail("cudaMalloc(twiddles) failed");
     if (cudaMemcpy(ctx->d_twid, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess)
         return bail("cudaMemcpy(twiddles) failed");
-    if (cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks_smem_bytes((int)p.ks_level)) != cudaSuccess)
-        return bail("cudaFuncSetAttribute(ks_kernel) failed");
+    {
+        const int ks_smem = (int)ks_smem_bytes((int)p.ks_level);
+        if (cudaFuncSetAttribute(ks_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ks_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(ks_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ks_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(ks_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ks_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(ks_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ks_smem) != cudaSuccess)
+            return bail("cudaFuncSetAttribute(ks_kernel) failed");
+    }
     *out = ctx;
     return 0;
 }

@@ -43,7 +43,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(kKsThreads, 2) ks_kernel(const KsArgs a) {
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(kKsThreads, MINB) ks_kernel(const KsArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int kc = kKsIC * a.level;
     uint64_t *ktile = reinterpret_cast<uint64_t *>(smem);                           // [2][kc][BN]
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kKsThreads, 2) ks_kernel(const KsArgs a) {
         __syncthreads();
         const uint64_t *kt = ktile + (size_t)buf * kc * kKsBN + tx * 4;
         const uint8_t *dt = dtile + (size_t)buf * kc * kKsBM + ty * 8;
-#pragma unroll 4
+#pragma unroll UNROLL
         for (int k = 0; k < kc; k++) {
             const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(kt + (size_t)k * kKsBN);
             const ulonglong2 k23 = *reinterpret_cast<const ulonglong2 *>(kt + (size_t)k * kKsBN + 2);

@@ -57,12 +57,13 @@ __device__ __forceinline__ uint32_t modswitch2048(uint64_t x) { return (uint32_t
 
 // closest_representable + the single balanced digit of level 1 (base 2^23):
 // commons/math/decomposition/decomposer.rs:98-116, iter.rs:120-127.  Only bits 63..40 of d matter.
-// Result as a double, converted exactly with the 2^52 + 2^31 biased-mantissa trick.
+// Result as a double (exact: |digit| <= 2^22).  The int -> double conversion is issued to the XU
+// pipe (I2F.F64.S32) on purpose: the FP64 pipe is the binding resource of this kernel.
 __device__ __forceinline__ double digit23_as_double(uint64_t d) {
     const uint32_t hi = (uint32_t)(d >> 32);
     const uint32_t t = (((hi >> 8) + 1u) >> 1) & 0x7FFFFFu;
     const int32_t dig = (int32_t)t - ((t > 0x400000u) ? 0x800000 : 0);
-    return __hiloint2double(0x43300000, (int)((uint32_t)dig ^ 0x80000000u)) - 4503601774854144.0;
+    return __int2double_rn(dig);
 }
 
 // from_torus, core_crypto/commons/math/torus/mod.rs:72-78 (round-half-even like the x86 SIMD path)
