@@ -125,6 +125,25 @@ int b200tfhe_get_kernel_times(b200tfhe_ctx *ctx, double *ks_ms, uint64_t *ks_lau
  * BSK read from L2 by every warp; 2 = 6 per CTA, BSK read from L2. */
 int b200tfhe_set_pbs_variant(b200tfhe_ctx *ctx, int variant);
 
+/* ---- batched call sites: level-synchronous programs ---------------------------------- */
+/* The reference's integer / FheString / Trivium layers issue vectors of independent (ciphertext,
+ * lookup table) pairs per dependency level (integer/server_key/radix_parallel/comparison.rs:22-28,
+ * add.rs:529-535, comparator.rs:257-288; examples/fhe_strings/server_key/{comparisons,change_case,
+ * contains,find}.rs; apps/trivium/src/trivium/trivium_bool.rs:143-227).  A program is that schedule
+ * compiled once for a workload shape: per level ONE lwe-linear launch + ONE ks_pbs_batch launch, all
+ * intermediate blocks resident in HBM.  Names and shapes: tfhe_rs_string_b200/csrc/programs.hpp
+ * ("radix_eq", "radix_add", "radix_sub", "radix_scalar_gt|lt|eq", "string_eq",
+ * "string_to_uppercase", "string_contains", "string_find", "trivium").  Inputs and outputs are
+ * arrays of big-key LWE blocks (k*N+1 u64 each). */
+typedef struct b200tfhe_program b200tfhe_program;
+int b200tfhe_program_create(b200tfhe_ctx *ctx, const char *op, const uint64_t *shape, size_t n_shape,
+                            b200tfhe_program **out);
+/* info[0..5] = n_inputs, n_outputs, n_pbs, depth, n_stages, n_luts */
+int b200tfhe_program_info(const b200tfhe_program *prog, uint64_t *info);
+int b200tfhe_program_run(b200tfhe_program *prog, const uint64_t *in, uint64_t *out);              /* host buffers, synchronous */
+int b200tfhe_program_run_device(b200tfhe_program *prog, const uint64_t *d_in, uint64_t *d_out);   /* device buffers, asynchronous */
+int b200tfhe_program_destroy(b200tfhe_program *prog);
+
 /* ---- unit-test hooks (exercise exactly the transforms the PBS kernel uses) ------------ */
 /* out[i] += a_int[i] (x) b_torus[i] in Z[X]/(X^2048+1); host buffers, count x 2048 u64 each.
  * Mirrors the reference's FFT product test, fft_impl/fft64/math/fft/tests.rs:82-222. */

@@ -14,6 +14,7 @@
 
 #include "ks_kernel.cuh"
 #include "pbs_kernel.cuh"
+#include "programs.hpp"
 
 using namespace b200;
 
@@ -556,6 +557,170 @@ int b200tfhe_set_pbs_variant(b200tfhe_ctx *ctx, int variant) {
     ARG_TRY(ctx, variant >= 0 && variant <= 2, "variant must be 0, 1 or 2");
     std::lock_guard<std::mutex> l(ctx->mu);
     ctx->pbs_variant = variant;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// level-synchronous programs
+}  // extern "C"
+
+struct b200tfhe_program {
+    b200tfhe_ctx *ctx = nullptr;
+    std::unique_ptr<Circuit> c;
+    int32_t *d_term_block = nullptr, *d_outputs = nullptr;
+    int64_t *d_term_coeff = nullptr;
+    uint32_t *d_node_tbeg = nullptr, *d_node_lut = nullptr;
+    uint64_t *d_node_pt = nullptr, *d_pool = nullptr, *d_stage = nullptr, *d_io = nullptr;
+    size_t max_stage = 0;
+};
+
+namespace {
+
+void program_free(b200tfhe_program *p) {
+    if (!p) return;
+    cudaFree(p->d_term_block); cudaFree(p->d_outputs); cudaFree(p->d_term_coeff); cudaFree(p->d_node_tbeg);
+    cudaFree(p->d_node_lut); cudaFree(p->d_node_pt); cudaFree(p->d_pool); cudaFree(p->d_stage); cudaFree(p->d_io);
+    delete p;
+}
+
+template <typename T>
+int upload(b200tfhe_ctx *ctx, T **dst, const std::vector<T> &src) {
+    const size_t bytes = std::max<size_t>(1, src.size()) * sizeof(T);
+    CU_TRY(ctx, cudaMalloc(dst, bytes));
+    if (!src.empty()) CU_TRY(ctx, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// inputs must already be in the pool's first n_inputs slots
+int program_execute(b200tfhe_program *p, uint64_t *d_out) {
+    b200tfhe_ctx *ctx = p->ctx;
+    const Circuit &c = *p->c;
+    const int size = (int)ctx->big_size();
+    const size_t n_in = c.n_inputs();
+    for (const Circuit::Stage &st : c.stages) {
+        const size_t n = st.end - st.begin;
+        uint64_t *dst_nodes = p->d_pool + (n_in + st.begin) * (size_t)size;
+        uint64_t *lin_out = st.bootstrap ? p->d_stage : dst_nodes;
+        for (size_t off = 0; off < n; off += 65535) {   // gridDim.y limit
+            const size_t cnt = std::min<size_t>(65535, n - off);
+            dim3 grid((size + 255) / 256, (unsigned)cnt);
+            lwe_lincomb_kernel<<<grid, 256, 0, ctx->stream>>>(p->d_pool, p->d_term_block, p->d_term_coeff, p->d_node_tbeg,
+                                                              p->d_node_pt, lin_out + off * (size_t)size,
+                                                              (int)(st.begin + off), size);
+        }
+        CU_TRY(ctx, cudaGetLastError());
+        if (st.bootstrap) {
+            if (int rc = ensure_workspace(ctx, n)) return rc;
+            if (int rc = launch_ks(ctx, p->d_stage, ctx->d_small, n)) return rc;
+            if (int rc = launch_pbs(ctx, ctx->d_small, p->d_node_lut + st.begin, dst_nodes, n)) return rc;
+        }
+    }
+    const size_t n_out = c.outputs.size();
+    for (size_t off = 0; off < n_out; off += 65535) {
+        const size_t cnt = std::min<size_t>(65535, n_out - off);
+        dim3 grid((size + 255) / 256, (unsigned)cnt);
+        lwe_gather_kernel<<<grid, 256, 0, ctx->stream>>>(p->d_pool, p->d_outputs + off, d_out + off * (size_t)size, size);
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200tfhe_program_create(b200tfhe_ctx *ctx, const char *op, const uint64_t *shape, size_t n_shape,
+                            b200tfhe_program **out) {
+    if (!out) return fail(ctx, "invalid argument: out is null");
+    *out = nullptr;
+    if (int rc = check_ready(ctx)) return rc;
+    ARG_TRY(ctx, op && (shape || n_shape == 0), "null pointer");
+    std::unique_ptr<Circuit> c;
+    try {
+        c = build_program(op, std::vector<uint64_t>(shape, shape + n_shape), ctx->p.message_modulus, ctx->p.carry_modulus);
+    } catch (const std::exception &e) {
+        return fail(ctx, std::string("program_create: ") + e.what());
+    }
+    auto *p = new b200tfhe_program();
+    p->ctx = ctx;
+    // lookup tables -> engine ids (content addressed, shared with every other user of the context)
+    std::vector<uint32_t> lut_ids(c->luts.size());
+    for (size_t l = 0; l < c->luts.size(); l++)
+        if (b200tfhe_register_lut_from_table(ctx, c->luts[l].data(), c->luts[l].size(), &lut_ids[l])) { program_free(p); return 1; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const uint64_t delta = ((uint64_t)1 << 63) / ((uint64_t)ctx->p.message_modulus * ctx->p.carry_modulus);
+    std::vector<int32_t> tb(c->terms.size());
+    std::vector<int64_t> tc(c->terms.size());
+    for (size_t t = 0; t < c->terms.size(); t++) { tb[t] = c->terms[t].block; tc[t] = c->terms[t].coeff; }
+    std::vector<uint32_t> tbeg(c->nodes.size() + 1), nlut(c->nodes.size());
+    std::vector<uint64_t> npt(c->nodes.size());
+    for (size_t k = 0; k < c->nodes.size(); k++) {
+        tbeg[k] = c->nodes[k].term_begin;
+        nlut[k] = c->nodes[k].lut >= 0 ? lut_ids[c->nodes[k].lut] : 0;
+        npt[k] = c->nodes[k].plaintext * delta;
+    }
+    tbeg[c->nodes.size()] = (uint32_t)c->terms.size();
+    for (const Circuit::Stage &st : c->stages)
+        if (st.bootstrap) p->max_stage = std::max<size_t>(p->max_stage, st.end - st.begin);
+    const size_t big = ctx->big_size();
+    int rc = upload(ctx, &p->d_term_block, tb);
+    if (!rc) rc = upload(ctx, &p->d_term_coeff, tc);
+    if (!rc) rc = upload(ctx, &p->d_node_tbeg, tbeg);
+    if (!rc) rc = upload(ctx, &p->d_node_lut, nlut);
+    if (!rc) rc = upload(ctx, &p->d_node_pt, npt);
+    if (!rc) rc = upload(ctx, &p->d_outputs, c->outputs);
+    auto alloc = [&](uint64_t **ptr, size_t n_blocks) {
+        if (rc) return;
+        cudaError_t e = cudaMalloc(ptr, std::max<size_t>(1, n_blocks) * big * sizeof(uint64_t));
+        if (e != cudaSuccess) rc = fail(ctx, std::string("cudaMalloc(program pool): ") + cudaGetErrorString(e));
+    };
+    alloc(&p->d_pool, c->n_blocks());
+    alloc(&p->d_stage, p->max_stage);
+    alloc(&p->d_io, c->outputs.size());
+    if (rc) { program_free(p); return rc; }
+    p->c = std::move(c);
+    *out = p;
+    return 0;
+}
+
+int b200tfhe_program_info(const b200tfhe_program *prog, uint64_t *info) {
+    if (!prog || !info) return fail(nullptr, "invalid argument: null pointer");
+    const Circuit &c = *prog->c;
+    info[0] = c.n_inputs(); info[1] = c.outputs.size(); info[2] = c.n_pbs(); info[3] = c.depth();
+    info[4] = c.stages.size(); info[5] = c.luts.size();
+    return 0;
+}
+
+int b200tfhe_program_run_device(b200tfhe_program *prog, const uint64_t *d_in, uint64_t *d_out) {
+    if (!prog) return fail(nullptr, "invalid argument: null program");
+    b200tfhe_ctx *ctx = prog->ctx;
+    if (int rc = check_ready(ctx)) return rc;
+    std::lock_guard<std::mutex> l(ctx->mu);
+    ARG_TRY(ctx, d_in && d_out, "null pointer");
+    CU_TRY(ctx, cudaMemcpyAsync(prog->d_pool, d_in, prog->c->n_inputs() * ctx->big_size() * sizeof(uint64_t),
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+    return program_execute(prog, d_out);
+}
+
+int b200tfhe_program_run(b200tfhe_program *prog, const uint64_t *in, uint64_t *out) {
+    if (!prog) return fail(nullptr, "invalid argument: null program");
+    b200tfhe_ctx *ctx = prog->ctx;
+    if (int rc = check_ready(ctx)) return rc;
+    std::lock_guard<std::mutex> l(ctx->mu);
+    ARG_TRY(ctx, in && out, "null pointer");
+    const size_t big_bytes = ctx->big_size() * sizeof(uint64_t);
+    CU_TRY(ctx, cudaMemcpyAsync(prog->d_pool, in, prog->c->n_inputs() * big_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = program_execute(prog, prog->d_io)) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(out, prog->d_io, prog->c->outputs.size() * big_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200tfhe_program_destroy(b200tfhe_program *prog) {
+    if (!prog) return 0;
+    cudaSetDevice(prog->ctx->device);
+    cudaStreamSynchronize(prog->ctx->stream);
+    program_free(prog);
     return 0;
 }
 

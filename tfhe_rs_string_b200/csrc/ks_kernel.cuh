@@ -200,4 +200,29 @@ __global__ void lwe_linear_kernel(const LinArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Stage kernels of the level executor: out[k] = sum_t coeff[t] * pool[block[t]] (+ plaintext on the
+// body) for every node k of one dependency level (generalises lwe_linear_kernel to CSR term lists),
+// and the final gather of the program outputs.
+__global__ void lwe_lincomb_kernel(const uint64_t *__restrict__ pool, const int32_t *__restrict__ term_block,
+                                   const int64_t *__restrict__ term_coeff, const uint32_t *__restrict__ node_tbeg,
+                                   const uint64_t *__restrict__ node_pt, uint64_t *__restrict__ out,
+                                   const int first_node, const int size) {
+    const int k = first_node + blockIdx.y;
+    const uint32_t t0 = node_tbeg[k], t1 = node_tbeg[k + 1];
+    uint64_t *o = out + (size_t)blockIdx.y * size;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < size; j += gridDim.x * blockDim.x) {
+        uint64_t v = (j == size - 1) ? node_pt[k] : 0;
+        for (uint32_t t = t0; t < t1; t++) v += (uint64_t)term_coeff[t] * pool[(size_t)term_block[t] * size + j];
+        o[j] = v;
+    }
+}
+__global__ void lwe_gather_kernel(const uint64_t *__restrict__ pool, const int32_t *__restrict__ ids,
+                                  uint64_t *__restrict__ out, const int size) {
+    const uint64_t *src = pool + (size_t)ids[blockIdx.y] * size;
+    uint64_t *o = out + (size_t)blockIdx.y * size;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < size; j += gridDim.x * blockDim.x) o[j] = src[j];
+}
+
 }  // namespace b200

@@ -17,6 +17,8 @@ EXPORTED_SYMBOLS = [
     "b200tfhe_lwe_linear_batch_device", "b200tfhe_sync", "b200tfhe_stream",
     "b200tfhe_set_profiling", "b200tfhe_get_kernel_times", "b200tfhe_set_pbs_variant",
     "b200tfhe_debug_negacyclic_mul",
+    "b200tfhe_program_create", "b200tfhe_program_info", "b200tfhe_program_run", "b200tfhe_program_run_device",
+    "b200tfhe_program_destroy",
 ]
 
 
@@ -93,6 +95,11 @@ def load_library():
                                       C.POINTER(C.c_uint64), C.c_int],
         "b200tfhe_set_pbs_variant": [ctx, C.c_int],
         "b200tfhe_debug_negacyclic_mul": [ctx, u64p, u64p, u64p, C.c_size_t],
+        "b200tfhe_program_create": [ctx, C.c_char_p, u64p, C.c_size_t, C.POINTER(C.c_void_p)],
+        "b200tfhe_program_info": [C.c_void_p, u64p],
+        "b200tfhe_program_run": [C.c_void_p, u64p, u64p],
+        "b200tfhe_program_run_device": [C.c_void_p, u64p, u64p],
+        "b200tfhe_program_destroy": [C.c_void_p],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -258,3 +265,43 @@ class Engine:
         assert out.dtype == np.uint64 and out.shape == a.shape and out.flags["C_CONTIGUOUS"]
         self._check(self.L.b200tfhe_debug_negacyclic_mul(self.h, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
         return out
+
+
+class Program:
+    """A batched call site (radix / FheString / Trivium operation) compiled for one workload shape:
+    b200tfhe_program_* in include/b200tfhe.h; names and shapes in csrc/programs.hpp."""
+
+    def __init__(self, engine, op, shape):
+        self.engine = engine
+        self.op, self.shape = op, list(shape)
+        sh = np.ascontiguousarray(shape, dtype=np.uint64)
+        h = C.c_void_p()
+        engine._check(engine.L.b200tfhe_program_create(engine.h, op.encode(), _ptr(sh), len(sh), C.byref(h)))
+        self.h = h
+        info = np.zeros(6, dtype=np.uint64)
+        engine._check(engine.L.b200tfhe_program_info(self.h, _ptr(info)))
+        self.info = dict(zip(["n_inputs", "n_outputs", "n_pbs", "depth", "n_stages", "n_luts"], (int(x) for x in info)))
+
+    def run(self, cts, out=None):
+        """Host buffers (numpy or pinned torch): H2D, all levels, D2H; synchronous."""
+        n_in, n_out, big = self.info["n_inputs"], self.info["n_outputs"], self.engine.params.big_lwe_size
+        if isinstance(cts, np.ndarray):
+            cts = np.ascontiguousarray(cts, dtype=np.uint64).reshape(n_in, big)
+            if out is None:
+                out = np.empty((n_out, big), dtype=np.uint64)
+        self.engine._check(self.engine.L.b200tfhe_program_run(self.h, _ptr(cts), _ptr(out)))
+        return out
+
+    def run_device(self, d_in, d_out):
+        self.engine._check(self.engine.L.b200tfhe_program_run_device(self.h, _ptr(d_in), _ptr(d_out)))
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.engine, "h", None):
+            self.engine.L.b200tfhe_program_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
