@@ -46,3 +46,17 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 for pat in (r'#include\s*[<"][^>"]*oracle', r'\bimport\s+oracle', r'\bfrom\s+oracle', r'liboracle', r'orc_\w+\s*\('):
                     assert not re.search(pat, txt), (f, pat)
+
+
+def test_rust_shim_declares_exactly_the_header_symbols():
+    """rust_shim/src/lib.rs cannot be compiled here (no cargo); keep its extern block in lock-step
+    with include/b200tfhe.h by name and by argument count."""
+    hdr = open(os.path.join(ROOT, "include", "b200tfhe.h")).read()
+    rs = open(os.path.join(ROOT, "rust_shim", "src", "lib.rs")).read()
+    ext = rs[rs.index('extern "C" {'):]
+    ext = ext[:ext.index("\n}\n")]
+    rust = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (b200tfhe_\w+)\s*\((.*?)\)\s*->\s*c_int;", ext, re.S)}
+    assert sorted(rust) == _header_symbols()
+    for name, args in rust.items():
+        c_args = re.search(r"\bint\s+" + name + r"\s*\((.*?)\)\s*;", hdr, re.S).group(1)
+        assert len([a for a in args.split(",") if a.strip()]) == len([a for a in c_args.split(",") if a.strip()]), name

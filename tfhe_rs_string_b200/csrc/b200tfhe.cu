@@ -205,6 +205,8 @@ int launch_pbs(b200tfhe_ctx *ctx, const uint64_t *d_small, const uint32_t *d_lut
     PbsArgs a{};
     a.lwe_small = d_small; a.lut_idx = d_lut_idx; a.luts = ctx->d_luts; a.bsk = ctx->d_bsk(); a.twid = ctx->d_twid;
     a.out = d_out; a.batch = (int)batch; a.n = (int)ctx->p.lwe_dimension;
+    static const int dev_skew = getenv("B200TFHE_PBS_SKEW") ? atoi(getenv("B200TFHE_PBS_SKEW")) : 0;  // development knob
+    a.skew_cycles = dev_skew;
     prof_begin(ctx, ctx->ev_pbs);
     int rc;
     switch (ctx->pbs_variant) {
