@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 FLOP_PER_PBS = 262144 * 742          # BASELINE.md section 2 / SURVEY 8d: algorithmic FP64 flop per PBS
 BSK_BYTES = 742 * 4 * 1024 * 16      # Fourier BSK streamed once per resident wave of ciphertexts
 KSK_BYTES = 2048 * 5 * 743 * 8
+KS_MACS = 2048 * 5 * 743 * 8          # s8 x u8 MACs per keyswitch on the tensor path (8 byte limbs per KSK word)
 METRIC = "KS+PBS/sec (PARAM_MESSAGE_2_CARRY_2)"
 UNIT = "KS+PBS/s"
 
@@ -37,7 +38,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="ciphertexts in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", type=int, default=0, help="PBS kernel variant (b200tfhe_set_pbs_variant)")
+    ap.add_argument("--variant", type=int, default=3, help="PBS kernel variant (b200tfhe_set_pbs_variant)")
     return ap.parse_args()
 
 
@@ -280,7 +281,8 @@ def run_b200(args):
             },
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "pbs_kernel", "kernel_ms": pbs_ms, "ks_kernel_ms": ks_ms,
+                "traffic": None, "kernel": "pbs_kernel3", "kernel_ms": pbs_ms, "ks_kernel_ms": ks_ms,
+                "ks_int8_TOPs": B * KS_MACS * 2 / (ks_ms * 1e-3) / 1e12,
                 "kernel_share_of_step": pbs_ms / ms_per_step, "peak_source": peak_src,
                 "algorithmic_flop_per_unit": FLOP_PER_PBS,
                 "bsk_stream_GBps": n_waves * BSK_BYTES / (pbs_ms * 1e-3) / 1e9,
@@ -289,7 +291,7 @@ def run_b200(args):
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * p.big_lwe_size * 8 + B * 4),
                     "d2h_bytes_per_step": int(B * p.big_lwe_size * 8), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
-            "gpu_launches": int(kt["pbs_launches"] + kt["ks_launches"]),
+            "gpu_launches": int(kt["pbs_launches"] + 2 * kt["ks_launches"]),   # per step: ks_digits + ks_mma + pbs
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

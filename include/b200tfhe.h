@@ -120,9 +120,10 @@ int b200tfhe_set_profiling(b200tfhe_ctx *ctx, int enabled);
 /* Accumulated device time (ms) and launch counts since the last reset; synchronises. */
 int b200tfhe_get_kernel_times(b200tfhe_ctx *ctx, double *ks_ms, uint64_t *ks_launches, double *pbs_ms,
                               uint64_t *pbs_launches, int reset);
-/* Selects the PBS kernel variant (all keep the accumulator in TMEM): 0 = default, 4 ciphertexts
- * per CTA, BSK slice staged once per CTA in shared memory by a bulk async copy; 1 = 4 per CTA,
- * BSK read from L2 by every warp; 2 = 6 per CTA, BSK read from L2. */
+/* Selects the PBS kernel variant (all keep the accumulator in TMEM; 4 ciphertexts per CTA unless
+ * stated): 3 = default (pbs_kernel3.cuh: biased accumulator, transform exchange); 0 = previous
+ * generation, BSK slice staged once per CTA in shared memory by a bulk async copy; 1 = BSK read
+ * from L2 by every warp; 2 = 6 ciphertexts per CTA, BSK read from L2. */
 int b200tfhe_set_pbs_variant(b200tfhe_ctx *ctx, int variant);
 
 /* ---- batched call sites: level-synchronous programs ---------------------------------- */

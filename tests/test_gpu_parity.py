@@ -63,7 +63,7 @@ def test_keyswitch_adversarial_inputs(engine, real_keys):
     assert np.array_equal(engine.keyswitch_batch(cts), real_keys.keyswitch_batch(cts))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_pbs_parity(engine, real_keys, variant):
     engine.set_pbs_variant(variant)
     try:
@@ -90,7 +90,7 @@ def test_pbs_parity(engine, real_keys, variant):
         assert 0.6 < e_gpu.std() / e_ref.std() < 1.6, (e_gpu.std(), e_ref.std())
         assert np.abs(e_gpu).max() < (1 << 54)
     finally:
-        engine.set_pbs_variant(0)
+        engine.set_pbs_variant(3)
 
 
 def test_ks_pbs_all_messages_full_batch(engine, real_keys):

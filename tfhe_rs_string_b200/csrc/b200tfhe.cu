@@ -13,7 +13,9 @@
 #include <vector>
 
 #include "ks_kernel.cuh"
+#include "ks_mma.cuh"
 #include "pbs_kernel.cuh"
+#include "pbs_kernel3.cuh"
 #include "programs.hpp"
 
 using namespace b200;
@@ -43,7 +45,8 @@ struct b200tfhe_ctx {
 
     // key arena: [Fourier BSK][KSK][colsum]
     unsigned char *arena = nullptr;
-    size_t arena_bytes = 0, off_bsk = 0, off_ksk = 0, off_colsum = 0;
+    size_t arena_bytes = 0, off_bsk = 0, off_ksk = 0, off_colsum = 0, off_ksk_limbs = 0;
+    KsMmaGeom ks_geom{};
     bool ksk_loaded = false, bsk_loaded = false;
     double2 *d_twid = nullptr;
 
@@ -56,9 +59,10 @@ struct b200tfhe_ctx {
     // workspace for the host-buffer entry points and the fused KS->PBS
     uint64_t *d_in = nullptr, *d_small = nullptr, *d_out = nullptr;
     uint32_t *d_lut_idx = nullptr;
+    uint8_t *d_digits = nullptr;   // keyswitch digits, tile order (ks_mma.cuh)
     size_t ws_cap = 0;
 
-    int pbs_variant = 0;
+    int pbs_variant = 3;
     bool profiling = false;
     std::vector<EventPair> ev_ks, ev_pbs;
     double ks_ms = 0, pbs_ms = 0;
@@ -74,6 +78,7 @@ struct b200tfhe_ctx {
     double2 *d_bsk() const { return reinterpret_cast<double2 *>(arena + off_bsk); }
     uint64_t *d_ksk() const { return reinterpret_cast<uint64_t *>(arena + off_ksk); }
     uint64_t *d_colsum() const { return reinterpret_cast<uint64_t *>(arena + off_colsum); }
+    uint8_t *d_ksk_limbs() const { return arena + off_ksk_limbs; }
 };
 
 namespace {
@@ -115,12 +120,13 @@ int ensure_workspace(b200tfhe_ctx *ctx, size_t batch) {
     if (batch <= ctx->ws_cap) return 0;
     size_t cap = std::max<size_t>(batch, 256);
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_in); cudaFree(ctx->d_small); cudaFree(ctx->d_out); cudaFree(ctx->d_lut_idx);
-    ctx->d_in = ctx->d_small = ctx->d_out = nullptr; ctx->d_lut_idx = nullptr; ctx->ws_cap = 0;
+    cudaFree(ctx->d_in); cudaFree(ctx->d_small); cudaFree(ctx->d_out); cudaFree(ctx->d_lut_idx); cudaFree(ctx->d_digits);
+    ctx->d_in = ctx->d_small = ctx->d_out = nullptr; ctx->d_lut_idx = nullptr; ctx->d_digits = nullptr; ctx->ws_cap = 0;
     CU_TRY(ctx, cudaMalloc(&ctx->d_in, cap * ctx->big_size() * sizeof(uint64_t)));
     CU_TRY(ctx, cudaMalloc(&ctx->d_small, cap * ctx->small_size() * sizeof(uint64_t)));
     CU_TRY(ctx, cudaMalloc(&ctx->d_out, cap * ctx->big_size() * sizeof(uint64_t)));
     CU_TRY(ctx, cudaMalloc(&ctx->d_lut_idx, cap * sizeof(uint32_t)));
+    CU_TRY(ctx, cudaMalloc(&ctx->d_digits, ctx->ks_geom.a_total_bytes(cap)));
     ctx->ws_cap = cap;
     return 0;
 }
@@ -172,7 +178,22 @@ int launch_ks(b200tfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, size_t b
     a.out_size = (int)ctx->small_size(); a.base_log = (int)ctx->p.ks_base_log; a.level = (int)ctx->p.ks_level;
     dim3 grid((a.out_size + kKsBN - 1) / kKsBN, (unsigned)((batch + kKsBM - 1) / kKsBM));
     prof_begin(ctx, ctx->ev_ks);
-    static const int dev_variant = getenv("B200TFHE_KS_VARIANT") ? atoi(getenv("B200TFHE_KS_VARIANT")) : 0;  // development knob
+    static const int dev_variant = getenv("B200TFHE_KS_VARIANT") ? atoi(getenv("B200TFHE_KS_VARIANT")) : -1;  // development knob
+    if (dev_variant < 0) {
+        // default: tensor-core path (ks_mma.cuh): digits pre-pass + s8 x u8 tcgen05 GEMM over the KSK byte limbs
+        if (int rc = ensure_workspace(ctx, batch)) return rc;
+        const KsMmaGeom &g = ctx->ks_geom;
+        const unsigned m_tiles = (unsigned)((batch + kKmM - 1) / kKmM);
+        ks_digits_kernel<<<dim3(g.k_stages, m_tiles), 256, g.a_stage_bytes(), ctx->stream>>>(d_in, ctx->d_digits, g, (int)batch);
+        KsMmaArgs m{};
+        m.a_tiled = ctx->d_digits; m.b_tiled = ctx->d_ksk_limbs(); m.in = d_in; m.out = d_out; m.g = g;
+        m.batch = (int)batch; m.stages = ks_mma_pipeline_stages(g);
+        ks_mma_kernel<<<dim3(g.n_tiles, m_tiles), 128, ks_mma_smem_bytes(g), ctx->stream>>>(m);
+        prof_end(ctx, ctx->ev_ks);
+        CU_TRY(ctx, cudaGetLastError());
+        ctx->ks_launches++;
+        return 0;
+    }
     const size_t smem = ks_smem_bytes(a.level);
     switch (dev_variant) {
         case 1: ks_kernel<4, 2><<<grid, kKsThreads, smem, ctx->stream>>>(a); break;
@@ -199,20 +220,53 @@ int launch_pbs_variant(b200tfhe_ctx *ctx, const PbsArgs &a) {
     return 0;
 }
 
+int launch_pbs3(b200tfhe_ctx *ctx, const PbsArgs &a) {
+    static bool configured[16] = {};
+    constexpr size_t smem = pbs3_smem_bytes();
+    if (!configured[ctx->device & 15]) {
+        CU_TRY(ctx, cudaFuncSetAttribute(pbs_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[ctx->device & 15] = true;
+    }
+    const unsigned grid = (unsigned)((a.batch + kCts3 - 1) / kCts3);
+#ifdef B200TFHE_TIMELINE
+    if (const char *dump = getenv("B200TFHE_PBS_TIMELINE")) {   // development: phase timestamps of CTA 0, steps 100..107
+        PbsArgs b = a;
+        const size_t n = 8 * 8 * 16;
+        CU_TRY(ctx, cudaMalloc(&b.dbg, n * sizeof(long long)));
+        CU_TRY(ctx, cudaMemsetAsync(b.dbg, 0, n * sizeof(long long), ctx->stream));
+        pbs_kernel3<<<grid, kCts3 * 64, smem, ctx->stream>>>(b);
+        std::vector<long long> h(n);
+        CU_TRY(ctx, cudaMemcpyAsync(h.data(), b.dbg, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(b.dbg);
+        if (FILE *f = fopen(dump, "w")) {
+            for (size_t r = 0; r < 64; r++) {
+                fprintf(f, "%zu %zu", r / 8, r % 8);
+                for (int k = 0; k < 11; k++) fprintf(f, " %lld", h[r * 16 + k]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+        return 0;
+    }
+#endif
+    pbs_kernel3<<<grid, kCts3 * 64, smem, ctx->stream>>>(a);
+    return 0;
+}
+
 int launch_pbs(b200tfhe_ctx *ctx, const uint64_t *d_small, const uint32_t *d_lut_idx, uint64_t *d_out, size_t batch) {
     if (!ctx->bsk_loaded) return fail(ctx, "bootstrap key not loaded");
     if (ctx->h_luts.empty()) return fail(ctx, "no lookup table registered");
     PbsArgs a{};
     a.lwe_small = d_small; a.lut_idx = d_lut_idx; a.luts = ctx->d_luts; a.bsk = ctx->d_bsk(); a.twid = ctx->d_twid;
     a.out = d_out; a.batch = (int)batch; a.n = (int)ctx->p.lwe_dimension;
-    static const int dev_skew = getenv("B200TFHE_PBS_SKEW") ? atoi(getenv("B200TFHE_PBS_SKEW")) : 0;  // development knob
-    a.skew_cycles = dev_skew;
     prof_begin(ctx, ctx->ev_pbs);
     int rc;
     switch (ctx->pbs_variant) {
         case 1: rc = launch_pbs_variant<4, false>(ctx, a); break;
         case 2: rc = launch_pbs_variant<6, false>(ctx, a); break;
-        default: rc = launch_pbs_variant<4, true>(ctx, a); break;
+        case 0: rc = launch_pbs_variant<4, true>(ctx, a); break;
+        default: rc = launch_pbs3(ctx, a); break;
     }
     prof_end(ctx, ctx->ev_pbs);
     if (rc) return rc;
@@ -275,6 +329,7 @@ int b200tfhe_ctx_create(const b200tfhe_params *params, int device, b200tfhe_ctx 
     auto *ctx = new b200tfhe_ctx();
     ctx->p = p;
     ctx->device = device;
+    if (const char *v = getenv("B200TFHE_PBS_VARIANT")) ctx->pbs_variant = atoi(v);   // development knob
     auto bail = [&](const std::string &m) {
         fail(nullptr, m);
         delete ctx;
@@ -285,7 +340,9 @@ int b200tfhe_ctx_create(const b200tfhe_params *params, int device, b200tfhe_ctx 
     ctx->off_bsk = 0;
     ctx->off_ksk = align_up(ctx->bsk_len() / 2 * sizeof(double2), 256);  // N/2 complex per poly
     ctx->off_colsum = ctx->off_ksk + align_up(ctx->ksk_len() * sizeof(uint64_t), 256);
-    ctx->arena_bytes = ctx->off_colsum + align_up(ctx->small_size() * sizeof(uint64_t), 256);
+    ctx->ks_geom = ks_mma_geom((int)(p.glwe_dimension * p.polynomial_size), (int)ctx->small_size(), (int)p.ks_level, (int)p.ks_base_log);
+    ctx->off_ksk_limbs = ctx->off_colsum + align_up(ctx->small_size() * sizeof(uint64_t), 256);
+    ctx->arena_bytes = ctx->off_ksk_limbs + align_up(ctx->ks_geom.b_total_bytes(), 256);
     if (cudaMalloc(&ctx->arena, ctx->arena_bytes) != cudaSuccess) return bail("cudaMalloc(key arena) failed");
     std::vector<double2> tw;
     make_twiddles(tw);
@@ -299,6 +356,11 @@ int b200tfhe_ctx_create(const b200tfhe_params *params, int device, b200tfhe_ctx 
             cudaFuncSetAttribute(ks_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ks_smem) != cudaSuccess ||
             cudaFuncSetAttribute(ks_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ks_smem) != cudaSuccess)
             return bail("cudaFuncSetAttribute(ks_kernel) failed");
+        if (ks_mma_pipeline_stages(ctx->ks_geom) < 2 || p.ks_level > (uint32_t)kKmMaxLevel)
+            return bail("unsupported parameters: keyswitch level too large for the tensor-core pipeline");
+        if (cudaFuncSetAttribute(ks_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks_mma_smem_bytes(ctx->ks_geom)) != cudaSuccess ||
+            cudaFuncSetAttribute(ks_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->ks_geom.a_stage_bytes()) != cudaSuccess)
+            return bail("cudaFuncSetAttribute(ks_mma_kernel) failed");
     }
     *out = ctx;
     return 0;
@@ -311,7 +373,7 @@ int b200tfhe_ctx_destroy(b200tfhe_ctx *ctx) {
     for (auto &e : ctx->ev_ks) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto &e : ctx->ev_pbs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaFree(ctx->arena); cudaFree(ctx->d_twid); cudaFree(ctx->d_luts);
-    cudaFree(ctx->d_in); cudaFree(ctx->d_small); cudaFree(ctx->d_out); cudaFree(ctx->d_lut_idx);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_small); cudaFree(ctx->d_out); cudaFree(ctx->d_lut_idx); cudaFree(ctx->d_digits);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -329,6 +391,8 @@ int b200tfhe_load_ksk(b200tfhe_ctx *ctx, const uint64_t *ksk, size_t n_u64) {
     dim3 grid((out_size + 127) / 128, 64);
     ks_colsum_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->d_ksk(), ctx->d_colsum(), n_rows, out_size,
                                                     (uint64_t)1 << (ctx->p.ks_base_log - 1));
+    CU_TRY(ctx, cudaGetLastError());
+    ksk_limbs_kernel<<<dim3(ctx->ks_geom.k_stages, ctx->ks_geom.n_tiles), kKmN, 0, ctx->stream>>>(ctx->d_ksk(), ctx->d_ksk_limbs(), ctx->ks_geom);
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->ksk_loaded = true;
@@ -556,7 +620,7 @@ int b200tfhe_get_kernel_times(b200tfhe_ctx *ctx, double *ks_ms, uint64_t *ks_lau
 
 int b200tfhe_set_pbs_variant(b200tfhe_ctx *ctx, int variant) {
     if (!ctx) return fail(nullptr, "null context");
-    ARG_TRY(ctx, variant >= 0 && variant <= 2, "variant must be 0, 1 or 2");
+    ARG_TRY(ctx, variant >= 0 && variant <= 3, "variant must be in [0, 3]");
     std::lock_guard<std::mutex> l(ctx->mu);
     ctx->pbs_variant = variant;
     return 0;

@@ -32,7 +32,7 @@ struct PbsArgs {
     uint64_t *out;              // [batch][2049]
     int batch;
     int n;
-    int skew_cycles;            // start delay of the second half of a CTA's ciphertexts (0 = none)
+    long long *dbg;             // development: per-warp phase timestamps of CTA 0 (nullptr = off)
 };
 
 constexpr int kMaxSmallDim = 1024;       // capacity of the per-ciphertext a~ table (u16 entries)
@@ -193,13 +193,6 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_kernel(const PbsArgs a) {
         tmem_wait_st();
         ct_barrier(1 + ctl);  // a~ table visible to both warps; rot copy visible within the warp
 
-        // De-phase the two ciphertexts that share an SM sub-partition (warps w and w + 4) by about half
-        // a CMUX step, so that one is in its FP64-bound transforms while the other does the integer /
-        // shared-memory phases.  The skew persists: the only coupling is the BSK slice hand-over.
-        if (a.skew_cycles > 0 && ctl >= CTS / 2) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < (long long)a.skew_cycles) {}
-        }
 
         // ---------------------------------------------------------------- CMUX loop
         // Steps with a~ = 0 (mod 2N) are not skipped as the reference does (bootstrap.rs:281): the

@@ -1,0 +1,304 @@
+// pbs_kernel3.cuh -- third generation of the batched programmable bootstrap (same contract and
+// reference citations as pbs_kernel.cuh; 4 ciphertexts per CTA, one warp per GLWE polynomial).
+//
+// What changed against pbs_kernel<4, true>:
+//   * The two warps of a ciphertext exchange their TRANSFORMS F_p (not partial products) through
+//     shared memory; warp p then forms its own output polynomial Out_p = B[p][p] F_p + B[1-p][p] F_{1-p}
+//     (update_with_fmadd, ggsw.rs:616-697) in place: no separate accumulation adds and half the
+//     live registers in the multiply.
+//   * The accumulator is kept as G = C - acc with C = 2^63 - 2^40 (TMEM, home layout) and as
+//     r = -acc (shared memory, rotation copy).  Then for x = rot - acc the reference's
+//     closest_representable + balanced digit (decomposer.rs:98-116, iter.rs:120-127) is exactly
+//         digit = (hi32(G + (+-rot)) >> 9) - (2^22 - 1)
+//     i.e. one 64-bit add, one shift and one exact int -> double conversion by exponent trick; the
+//     tie (x = 2^63 - 2^40 mod 2^64 -> +2^22, not -2^22) comes out right by construction.
+//   * The rotated gather uses the fact that, for one lane, the 32 indices (idx0 + 32 m) mod 2N cross
+//     a multiple of N at most once: one compare per element selects both the wrapped address and the
+//     negacyclic sign (polynomial_algorithms.rs:425-491).
+//   * from_torus scales by 2^64 with an exponent add instead of a DMUL (the FP64 pipe is the
+//     binding resource).
+#pragma once
+#include "pbs_kernel.cuh"
+
+namespace b200 {
+
+constexpr uint64_t kAccC = 0x7FFFFF0000000000ull;     // C = 2^63 - 2^40
+constexpr uint32_t kTmemAcc0 = 128, kTmemXchg = 384;   // column offsets inside a quadrant
+
+// ---- TMEM accessors without a "memory" clobber: ordering is carried by the register operands, so
+// the compiler stays free to schedule shared-memory loads across them.
+__device__ __forceinline__ void tmem_ld16_nc(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+__device__ __forceinline__ void tmem_st16_nc(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :
+                 : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
+}
+
+__device__ __forceinline__ double dbl(const uint32_t lo, const uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
+__device__ __forceinline__ void undbl(const double d, uint32_t &lo, uint32_t &hi) {
+    lo = (uint32_t)__double2loint(d); hi = (uint32_t)__double2hiint(d);
+}
+
+// from_torus (torus/mod.rs:72-78; round-half-even like fft/x86.rs:864): fractional part centred at
+// 0, times 2^64 by adding 64 to the exponent field (f is 0 or |f| >= 2^-1022; +-0 / subnormal
+// inputs become < 2^-950 and convert to 0), rounded to i64.
+__device__ __forceinline__ uint64_t from_torus_exp(const double x) {
+    const double f = x - rint(x);
+    const double s = __hiloint2double(__double2hiint(f) + (64 << 20), __double2loint(f));
+    return (uint64_t)__double2ll_rn(s);
+}
+
+// Development aid (tools/timeline.py): compile with -DB200TFHE_TIMELINE to record per-warp phase
+// timestamps of CTA 0, CMUX steps 100..107, into PbsArgs::dbg.
+#ifdef B200TFHE_TIMELINE
+#define PBS3_TS(k) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && i >= 100 && i < 108) a.dbg[((i - 100) * 8 + warp) * 16 + (k)] = clock64(); } while (0)
+#else
+#define PBS3_TS(k) do { } while (0)
+#endif
+constexpr int kCts3 = 4;
+__host__ __device__ constexpr size_t pbs3_smem_bytes() {
+    return kPbsHeaderBytes + kBskSliceBytes + (size_t)kCts3 * pbs_ct_smem_bytes();
+}
+
+__global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ctl = warp >> 1, p = warp & 1;
+    const int ct = blockIdx.x * kCts3 + ctl;
+    const bool active = ct < a.batch;
+
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem);
+    uint64_t *bsk_bar = reinterpret_cast<uint64_t *>(smem + 8);
+    unsigned int *consumed = reinterpret_cast<unsigned int *>(smem + 16);
+    double2 *bsk_s = reinterpret_cast<double2 *>(smem + kPbsHeaderBytes);
+    unsigned char *ctbase = smem + kPbsHeaderBytes + kBskSliceBytes + (size_t)ctl * pbs_ct_smem_bytes();
+    double2 *tb_own = reinterpret_cast<double2 *>(ctbase) + p * kTBufElems;
+    const double2 *tb_oth = reinterpret_cast<double2 *>(ctbase) + (1 - p) * kTBufElems;
+    uint16_t *ahat = reinterpret_cast<uint16_t *>(ctbase + (size_t)2 * kTBufElems * sizeof(double2));
+    uint64_t *rot = reinterpret_cast<uint64_t *>(tb_own);  // rotation copy (r = -acc) aliases the transposition buffer
+
+    // ---------------------------------------------------------------- CTA setup
+    if (warp == 0) tmem_alloc(slot, 512);
+    if (threadIdx.x == 0) {
+        mbar_init(bsk_bar, 1);
+        *consumed = 0;
+    }
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t tbase = *slot;
+    const uint32_t tquad = tbase + (((uint32_t)(warp & 3) * 32u) << 16);
+    const uint32_t t_acc = tquad + kTmemAcc0 + (uint32_t)(warp >> 2) * 128u;
+    const TmemTwiddles tw{tquad};
+    if (warp < 4) {   // one warp per TMEM quadrant stores its lanes' twiddle columns
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint32_t r[16];
+            GlobalTwiddles{a.twid, lane}.issue(c, r);
+            tmem_st16(tquad + c * 16, r);
+        }
+        tmem_wait_st();
+    }
+    const int n_act_cts = min(kCts3, a.batch - (int)blockIdx.x * kCts3);
+    const unsigned int n_act_warps = 2u * (unsigned int)n_act_cts;
+    if (threadIdx.x == 0) issue_bsk_slice(bsk_s, a.bsk, 0, bsk_bar);
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+
+    if (active) {
+        // ---------------------------------------------------------------- prologue
+        const uint64_t *lwe = a.lwe_small + (size_t)ct * (a.n + 1);
+        for (int i = p * 32 + lane; i < a.n; i += 64) ahat[i] = (uint16_t)modswitch2048(lwe[i]);
+        const uint32_t bhat = modswitch2048(lwe[a.n]);
+        const uint64_t *lut = a.luts + ((size_t)(a.lut_idx ? a.lut_idx[ct] : 0u) * 2 + p) * kN;
+        // acc = LUT * X^-b~: polynomial_wrapping_monic_monomial_div (polynomial_algorithms.rs:315-354)
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint32_t h[16];
+#pragma unroll
+            for (int mm = 0; mm < 4; mm++) {
+                const int j = lane + 32 * (c * 4 + mm);
+                const uint32_t i0 = (uint32_t)(j + bhat) & 4095u, i1 = (i0 + 1024u) & 4095u;
+                uint64_t v0 = lut[i0 & 2047u], v1 = lut[i1 & 2047u];
+                if (i0 & 2048u) v0 = 0 - v0;
+                if (i1 & 2048u) v1 = 0 - v1;
+                rot[j] = 0 - v0; rot[j + kHalf] = 0 - v1;
+                const uint64_t g0 = kAccC - v0, g1 = kAccC - v1;
+                h[4 * mm] = (uint32_t)g0; h[4 * mm + 1] = (uint32_t)(g0 >> 32);
+                h[4 * mm + 2] = (uint32_t)g1; h[4 * mm + 3] = (uint32_t)(g1 >> 32);
+            }
+            tmem_st16(t_acc + c * 16, h);
+        }
+        tmem_wait_st();
+        ct_barrier(1 + ctl);  // a~ table visible to both warps; rot copy visible within the warp
+
+        // ---------------------------------------------------------------- CMUX loop
+        // Steps with a~ = 0 (mod 2N) are not skipped as the reference does (bootstrap.rs:281): the
+        // rotation is then the identity, every digit is 0 and the step adds exactly zero.
+        for (int i = 0; i < a.n; i++) {
+            PBS3_TS(0);
+            double xr[32], xi[32];
+            // phase A: ct1 = acc * X^a~ - acc (polynomial_algorithms.rs:425-491), round + digit
+            // (ggsw.rs:514-521), exact int -> double, twist by C_m (fft/mod.rs:220-239)
+            {
+                const uint32_t ah = ahat[i];
+                const uint32_t base0 = (uint32_t)(lane + 4096 - (int)ah) & 4095u;   // source index of coefficient `lane`
+                const uint32_t base1 = (base0 + 1024u) & 4095u;                     // ... of coefficient `lane + 1024`
+                const uint32_t pos0 = base0 & 2047u, pos1 = base1 & 2047u;
+                // V = +acc_src when the source index is < N, -acc_src otherwise; with r = -acc stored:
+                // V = r ^ T - T with T = 0 (take r: source negated) or ~0 (take -r).
+                const uint32_t tn0 = (base0 & 2048u) ? 0u : 0xFFFFFFFFu, tn1 = (base1 & 2048u) ? 0u : 0xFFFFFFFFu;
+                const int mc0 = (int)((2048u - pos0 + 31u) >> 5), mc1 = (int)((2048u - pos1 + 31u) >> 5);  // first m past the wrap
+                const uint64_t *pn0 = rot + pos0, *pn1 = rot + pos1;
+                uint32_t h0[16], h1[16];
+                tmem_ld16_nc(t_acc, h0);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t(&h)[16] = (c & 1) ? h1 : h0;
+                    tmem_wait_ld16(h);
+                    if (c < 7) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
+#pragma unroll
+                    for (int mm = 0; mm < 4; mm++) {
+                        const int m = c * 4 + mm;
+                        const bool w0 = m >= mc0, w1 = m >= mc1;
+                        const uint64_t r0 = (w0 ? pn0 - kN : pn0)[32 * m], r1 = (w1 ? pn1 - kN : pn1)[32 * m];
+                        const uint32_t t0 = w0 ? ~tn0 : tn0, t1 = w1 ? ~tn1 : tn1;
+                        const uint64_t T0 = pack64(t0, t0), T1 = pack64(t1, t1);
+                        const uint64_t e0 = pack64(h[4 * mm], h[4 * mm + 1]) + (r0 ^ T0) - T0;
+                        const uint64_t e1 = pack64(h[4 * mm + 2], h[4 * mm + 3]) + (r1 ^ T1) - T1;
+                        // digit + (2^22 - 1) in [0, 2^23) -> double by exponent trick (exact)
+                        double fr = dbl((uint32_t)(e0 >> 41), 0x43300000u) - 4503599631564799.0;
+                        double fi = dbl((uint32_t)(e1 >> 41), 0x43300000u) - 4503599631564799.0;
+                        twist_m(fr, fi, m);
+                        xr[brev5(m)] = fr; xi[brev5(m)] = fi;
+                    }
+                }
+            }
+            __syncwarp();  // all rotation reads done before the buffer is reused for the transposition
+            PBS3_TS(1);
+
+            fwd1024(xr, xi, tb_own, tw, lane);
+            PBS3_TS(2);
+
+            // exchange the transforms; Out_p = B[p][p] * F_p + B[1-p][p] * F_{1-p}, written into the
+            // bit-reversed slot the inverse transform wants.  The own product needs nothing from the
+            // sibling, so it is formed before the barrier and hides the hand-over.
+#pragma unroll
+            for (int q = 0; q < 32; q++) tb_own[q * 32 + lane] = make_double2(xr[q], xi[q]);
+            PBS3_TS(3);
+            mbar_wait(bsk_bar, (uint32_t)(i & 1));
+            PBS3_TS(4);
+            double zr[32], zi[32];
+            {
+                const double2 *b_own = bsk_s + (size_t)(p * 2 + p) * kHalf + lane;         // row p, column p
+#pragma unroll
+                for (int q = 0; q < 32; q++) {
+                    const double2 bo = b_own[q * 32];
+                    zr[brev5(q)] = fma(-bo.y, xi[q], bo.x * xr[q]);
+                    zi[brev5(q)] = fma(bo.y, xr[q], bo.x * xi[q]);
+                }
+            }
+            PBS3_TS(5);
+            ct_barrier(1 + ctl);
+            PBS3_TS(6);
+            {
+                const double2 *b_oth = bsk_s + (size_t)((1 - p) * 2 + p) * kHalf + lane;   // row 1-p, column p
+#pragma unroll
+                for (int q = 0; q < 32; q++) {
+                    const double2 bx = b_oth[q * 32], g = tb_oth[q * 32 + lane];
+                    double o_r = fma(bx.x, g.x, zr[brev5(q)]), o_i = fma(bx.x, g.y, zi[brev5(q)]);
+                    zr[brev5(q)] = fma(-bx.y, g.y, o_r); zi[brev5(q)] = fma(bx.y, g.x, o_i);
+                }
+            }
+            PBS3_TS(7);
+            // this warp is done with the slice; the last of the CTA's warps refills the buffer
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned int old = atomicAdd(consumed, 1u);
+                if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
+                    issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
+            }
+            ct_barrier(1 + ctl);   // the sibling has read this warp's transform before the buffer is reused
+            PBS3_TS(8);
+
+            inv1024(zr, zi, tb_own, tw, lane);
+            __syncwarp();  // transposition reads done before the rotation copy overwrites the buffer
+            PBS3_TS(9);
+
+            // phase D: untwist, from_torus, wrapping add (fft/mod.rs:285-304), refresh both copies.
+            // D1 converts all 64 values first (64 independent chains through the conversion unit, no
+            // ordering points in between), D2 then streams the accumulator through TMEM.
+            uint64_t dl0[32], dl1[32];
+#pragma unroll
+            for (int m = 0; m < 32; m++) {
+                double yr = zr[m], yi = zi[m];
+                untwist_m(yr, yi, m);
+                dl0[m] = from_torus_exp(yr); dl1[m] = from_torus_exp(yi);
+            }
+            {
+                uint32_t h0[16], h1[16];
+                tmem_ld16_nc(t_acc, h0);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t(&h)[16] = (c & 1) ? h1 : h0;
+                    tmem_wait_ld16(h);
+                    if (c < 7) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
+#pragma unroll
+                    for (int mm = 0; mm < 4; mm++) {
+                        const int m = c * 4 + mm;
+                        const int j = lane + 32 * m;
+                        // acc += delta  <=>  G -= delta, r = G - C
+                        const uint64_t g0 = pack64(h[4 * mm], h[4 * mm + 1]) - dl0[m];
+                        const uint64_t g1 = pack64(h[4 * mm + 2], h[4 * mm + 3]) - dl1[m];
+                        rot[j] = g0 - kAccC; rot[j + kHalf] = g1 - kAccC;
+                        h[4 * mm] = (uint32_t)g0; h[4 * mm + 1] = (uint32_t)(g0 >> 32);
+                        h[4 * mm + 2] = (uint32_t)g1; h[4 * mm + 3] = (uint32_t)(g1 >> 32);
+                    }
+                    tmem_st16_nc(t_acc + c * 16, h);
+                }
+                tmem_wait_st();
+            }
+            __syncwarp();  // rotation copy complete before the next step's gather
+            PBS3_TS(10);
+        }
+
+        // ---------------------------------------------------------------- sample extraction
+        uint64_t *o = a.out + (size_t)ct * (kN + 1);
+        if (p == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                uint32_t h[16];
+                tmem_ld16(t_acc + c * 16, h);
+                tmem_wait_ld();
+#pragma unroll
+                for (int mm = 0; mm < 4; mm++) {
+                    const int j = lane + 32 * (c * 4 + mm);
+                    const uint64_t a0 = kAccC - pack64(h[4 * mm], h[4 * mm + 1]);
+                    const uint64_t a1 = kAccC - pack64(h[4 * mm + 2], h[4 * mm + 3]);
+                    if (j == 0) o[0] = a0; else o[kN - j] = 0 - a0;
+                    o[kHalf - j] = 0 - a1;  // coefficient j + 1024 -> index N - (j + 1024)
+                }
+            }
+        } else {
+            uint32_t h[16];
+            tmem_ld16(t_acc, h);
+            tmem_wait_ld();
+            if (lane == 0) o[kN] = kAccC - pack64(h[0], h[1]);
+        }
+    }
+
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace b200
