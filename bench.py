@@ -109,21 +109,38 @@ def measure_fp64_peak():
     return 34.07, "fallback: microbench dfma measured on this pool's B200 (profiles/r01_microbench.jsonl)"
 
 
-def cpu_baseline(sample, threads):
-    """The oracle port (oracle/tfhe_oracle.cpp: same algorithm as the reference's CPU path, one
-    ciphertext per thread like benches/core_crypto/pbs_bench.rs:517-531) on the host cores."""
+def _cpu_setup(threads):
     import numpy as np
     from oracle import oracle as O
     p = O.params_message_2_carry_2()
     keys = O.Keyset(p, seed=0xB200, n_threads=threads)
-    cts = keys.encrypt_batch(np.arange(sample) % 16, seed=0xC0FFEE)
     lut = keys.lut(lambda x: x)
+    return np, keys, lut
+
+
+def _cpu_calibrated_sample(np, keys, lut, threads, target_s, cap):
+    """Sizes the bounded CPU sample so one pass takes about `target_s` seconds on this host."""
+    n0 = 2 * threads
+    cts = keys.encrypt_batch(np.arange(n0) % 16, seed=0xC0FFEE)
     keys.ks_pbs_batch(cts[:threads], lut, n_threads=threads)          # warm caches / page in keys
+    t0 = time.perf_counter()
+    keys.ks_pbs_batch(cts, lut, n_threads=threads)
+    rate = n0 / (time.perf_counter() - t0)
+    return int(max(n0, min(cap, threads * round(rate * target_s / threads))))
+
+
+def cpu_baseline(sample, threads, cap):
+    """The oracle port (oracle/tfhe_oracle.cpp: same algorithm as the reference's CPU path, one
+    ciphertext per thread like benches/core_crypto/pbs_bench.rs:517-531) on the host cores."""
+    np, keys, lut = _cpu_setup(threads)
+    if not sample:
+        sample = _cpu_calibrated_sample(np, keys, lut, threads, 12.0, cap)
+    cts = keys.encrypt_batch(np.arange(sample) % 16, seed=0xC0FFEE)
     t0 = time.perf_counter()
     out = keys.ks_pbs_batch(cts, lut, n_threads=threads)
     dt = time.perf_counter() - t0
     ok = bool((keys.decrypt_batch(out) == (np.arange(sample) % 16)).all())
-    return sample / dt, dt, ok
+    return sample / dt, dt, ok, sample
 
 
 def run_reference(args):
@@ -131,15 +148,10 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = args.cpu_sample or max(32, min(256, 2 * threads))
-    import numpy as np
-    from oracle import oracle as O
-    p = O.params_message_2_carry_2()
-    keys = O.Keyset(p, seed=0xB200, n_threads=threads)
+    np, keys, lut = _cpu_setup(threads)
+    # each step = a bounded sample of the batch sized for ~10 s of host work (whole run: a few minutes)
+    sample = args.cpu_sample or _cpu_calibrated_sample(np, keys, lut, threads, 10.0, args.batch)
     cts = keys.encrypt_batch(np.arange(sample) % 16, seed=0xC0FFEE)
-    lut = keys.lut(lambda x: x)
-    for _ in range(max(1, min(args.warmup, 1))):
-        keys.ks_pbs_batch(cts[:threads], lut, n_threads=threads)
     steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -187,15 +199,8 @@ def run_b200(args):
         eng.load_ksk(rng.integers(0, 2**64, 2048 * 5 * 743, dtype=np.uint64))
         eng.load_bsk_standard(rng.integers(0, 2**64, 742 * 4 * 2048, dtype=np.uint64))
     if world > 1:
-        ptr, nbytes = eng.key_arena()
-
-        class _Arena:
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-        arena = torch.as_tensor(_Arena(), device=f"cuda:{local}")
-        dist.broadcast(arena, src=0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            eng.keys_adopt()
+        from tfhe_rs_string_b200 import multigpu
+        multigpu.broadcast_server_key(eng, dist, rank, f"cuda:{local}", src=0)
     key_setup_s = time.perf_counter() - t_key0
 
     # ---- synthetic inputs of the named shape (uniform u64 LWE words are what ciphertexts look like)
@@ -296,10 +301,9 @@ def run_b200(args):
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            sample = args.cpu_sample or max(32, min(256, 2 * threads))
-            v, dt, ok = cpu_baseline(sample, threads)
+            v, dt, ok, sample = cpu_baseline(args.cpu_sample, threads, B)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{sample} of the {B} ciphertexts, identity LUT, {dt:.1f} s, decrypt ok={ok}"}
+                                    "sample": f"{sample} of the {B} ciphertexts, identity LUT, {dt:.1f} s on {threads} host threads, decrypt ok={ok}"}
         print(json.dumps(line))
     eng.close()
     if dist is not None:
