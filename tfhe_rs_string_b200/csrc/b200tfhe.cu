@@ -220,21 +220,22 @@ int launch_pbs_variant(b200tfhe_ctx *ctx, const PbsArgs &a) {
     return 0;
 }
 
-int launch_pbs3(b200tfhe_ctx *ctx, const PbsArgs &a) {
+template <int CTS>
+int launch_pbs3_cts(b200tfhe_ctx *ctx, const PbsArgs &a) {
     static bool configured[16] = {};
-    constexpr size_t smem = pbs3_smem_bytes();
+    constexpr size_t smem = pbs3_smem_bytes<CTS>();
     if (!configured[ctx->device & 15]) {
-        CU_TRY(ctx, cudaFuncSetAttribute(pbs_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(ctx, cudaFuncSetAttribute(pbs_kernel3<CTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[ctx->device & 15] = true;
     }
-    const unsigned grid = (unsigned)((a.batch + kCts3 - 1) / kCts3);
+    const unsigned grid = (unsigned)((a.batch + CTS - 1) / CTS);
 #ifdef B200TFHE_TIMELINE
     if (const char *dump = getenv("B200TFHE_PBS_TIMELINE")) {   // development: phase timestamps of CTA 0, steps 100..107
         PbsArgs b = a;
         const size_t n = 8 * 8 * 16;
         CU_TRY(ctx, cudaMalloc(&b.dbg, n * sizeof(long long)));
         CU_TRY(ctx, cudaMemsetAsync(b.dbg, 0, n * sizeof(long long), ctx->stream));
-        pbs_kernel3<<<grid, kCts3 * 64, smem, ctx->stream>>>(b);
+        pbs_kernel3<CTS><<<grid, CTS * 64, smem, ctx->stream>>>(b);
         std::vector<long long> h(n);
         CU_TRY(ctx, cudaMemcpyAsync(h.data(), b.dbg, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -250,8 +251,25 @@ int launch_pbs3(b200tfhe_ctx *ctx, const PbsArgs &a) {
         return 0;
     }
 #endif
-    pbs_kernel3<<<grid, kCts3 * 64, smem, ctx->stream>>>(a);
+    pbs_kernel3<CTS><<<grid, CTS * 64, smem, ctx->stream>>>(a);
     return 0;
+}
+
+// Ciphertexts per CTA: the fewest that still fit the batch into the minimum number of waves over the
+// SMs (one CTA per SM).  Large batches get 4 (throughput); a dependency level with few bootstraps
+// gets 1-3, which shortens every CMUX step (fewer warps share an SM sub-partition) and so the
+// latency of the level.
+int launch_pbs3(b200tfhe_ctx *ctx, const PbsArgs &a) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const long long waves = (a.batch + 4LL * sms - 1) / (4LL * sms);
+    const long long per_cta = (a.batch + waves * sms - 1) / (waves * sms);
+    switch ((int)per_cta) {
+        case 1: return launch_pbs3_cts<1>(ctx, a);
+        case 2: return launch_pbs3_cts<2>(ctx, a);
+        case 3: return launch_pbs3_cts<3>(ctx, a);
+        default: return launch_pbs3_cts<4>(ctx, a);
+    }
 }
 
 int launch_pbs(b200tfhe_ctx *ctx, const uint64_t *d_small, const uint32_t *d_lut_idx, uint64_t *d_out, size_t batch) {

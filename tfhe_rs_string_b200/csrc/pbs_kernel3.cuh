@@ -49,7 +49,8 @@ __device__ __forceinline__ void undbl(const double d, uint32_t &lo, uint32_t &hi
 
 // from_torus (torus/mod.rs:72-78; round-half-even like fft/x86.rs:864): fractional part centred at
 // 0, times 2^64 by adding 64 to the exponent field (f is 0 or |f| >= 2^-1022; +-0 / subnormal
-// inputs become < 2^-950 and convert to 0), rounded to i64.
+// inputs become < 2^-950 and convert to 0), rounded to i64.  (Measured: replacing the F2I by an
+// all-FP64 split conversion does not shorten the phase.)
 __device__ __forceinline__ uint64_t from_torus_exp(const double x) {
     const double f = x - rint(x);
     const double s = __hiloint2double(__double2hiint(f) + (64 << 20), __double2loint(f));
@@ -63,11 +64,14 @@ __device__ __forceinline__ uint64_t from_torus_exp(const double x) {
 #else
 #define PBS3_TS(k) do { } while (0)
 #endif
-constexpr int kCts3 = 4;
+// kCts3 ciphertexts per CTA: 4 for throughput; 1..3 for small batches (fewer warps per SM sub-partition
+// shorten the per-step critical path, see launch_pbs3), always one CTA per SM.
+template <int kCts3>
 __host__ __device__ constexpr size_t pbs3_smem_bytes() {
     return kPbsHeaderBytes + kBskSliceBytes + (size_t)kCts3 * pbs_ct_smem_bytes();
 }
 
+template <int kCts3>
 __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,7 +90,8 @@ __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
     uint64_t *rot = reinterpret_cast<uint64_t *>(tb_own);  // rotation copy (r = -acc) aliases the transposition buffer
 
     // ---------------------------------------------------------------- CTA setup
-    if (warp == 0) tmem_alloc(slot, 512);
+    constexpr uint32_t kTmemCols = kCts3 <= 2 ? 256u : 512u;   // twiddles + 128 accumulator columns per warp of a quadrant
+    if (warp == 0) tmem_alloc(slot, kTmemCols);
     if (threadIdx.x == 0) {
         mbar_init(bsk_bar, 1);
         *consumed = 0;
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
 
     tmem_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 512);
+    if (warp == 0) tmem_dealloc(tbase, kTmemCols);
 }
 
 }  // namespace b200
