@@ -273,6 +273,13 @@ def run_b200(args):
         peak, peak_src = measure_fp64_peak()
         achieved = B * FLOP_PER_PBS / (pbs_ms * 1e-3) / 1e12
         n_waves = -(-B // (148 * 4))
+        traffic = None
+        try:   # DRAM bytes of the dominant kernel from the committed ncu --set full capture (same batch only)
+            m = json.load(open(os.path.join(ROOT, "profiles", "r01_final_ncu_metrics.json")))["pbs_kernel3<4>"]
+            if m["batch"] == B:
+                traffic = m["dram_bytes_read"] + m["dram_bytes_write"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -286,7 +293,8 @@ def run_b200(args):
             },
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "pbs_kernel3", "kernel_ms": pbs_ms, "ks_kernel_ms": ks_ms,
+                "traffic": traffic, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_final_ncu_metrics.json",
+                "kernel": "pbs_kernel3", "kernel_ms": pbs_ms, "ks_kernel_ms": ks_ms,
                 "ks_int8_TOPs": B * KS_MACS * 2 / (ks_ms * 1e-3) / 1e12,
                 "kernel_share_of_step": pbs_ms / ms_per_step, "peak_source": peak_src,
                 "algorithmic_flop_per_unit": FLOP_PER_PBS,
