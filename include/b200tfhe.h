@@ -97,10 +97,17 @@ int b200tfhe_pbs_batch(b200tfhe_ctx *ctx, const uint64_t *in, const uint32_t *lu
  * in/out: batch x (k*N+1); in == out allowed. */
 int b200tfhe_ks_pbs_batch(b200tfhe_ctx *ctx, const uint64_t *in, const uint32_t *lut_id, uint64_t *out, size_t batch);
 
+/* ServerKey::programmable_bootstrap_keyswitch_assign (shortint/server_key/mod.rs:859-933) ==
+ * apply_lookup_table_assign for PBSOrder::BootstrapKeyswitch (:471-474, e.g.
+ * PARAM_MESSAGE_2_CARRY_2_PBS_KS, shortint/parameters/mod.rs:1155-1169), batched: bootstrap the small
+ * ciphertext, then keyswitch the result back.  in/out: batch x (n+1); in == out allowed. */
+int b200tfhe_pbs_ks_batch(b200tfhe_ctx *ctx, const uint64_t *in, const uint32_t *lut_id, uint64_t *out, size_t batch);
+
 /* ---- hot path, device buffers (asynchronous on the context stream) -------------------- */
 int b200tfhe_keyswitch_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, uint64_t *d_out, size_t batch);
 int b200tfhe_pbs_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const uint32_t *d_lut_id, uint64_t *d_out, size_t batch);
 int b200tfhe_ks_pbs_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const uint32_t *d_lut_id, uint64_t *d_out, size_t batch);
+int b200tfhe_pbs_ks_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const uint32_t *d_lut_id, uint64_t *d_out, size_t batch);
 /* lwe_linear_algebra.rs (:68 add, :276 plaintext add, :556 cleartext mul, :703 sub) and the
  * bivariate pack (shortint/server_key/bivariate_pbs.rs:173-181), one launch:
  *   out[b] = ca[b] * x[ia[b]] + cb[b] * y[ib[b]];  out[b].body += pt[b]

@@ -126,6 +126,16 @@ def params_message_2_carry_2():
     return p
 
 
+def params_message_2_carry_2_pbs_ks():
+    """PARAM_MESSAGE_2_CARRY_2_PBS_KS (shortint/parameters/mod.rs:1155-1169): PBS -> KS order."""
+    p = params_message_2_carry_2()
+    p.lwe_dimension = 870
+    p.lwe_modular_std_dev = 0.0000006791658447437413
+    p.glwe_modular_std_dev = 0.00000000000000029403601535432533
+    p.ks_base_log, p.ks_level = 4, 4
+    return p
+
+
 def params_toy(n=16, N=256):
     p = Params()
     lib().orc_params_toy(C.byref(p), n, N)

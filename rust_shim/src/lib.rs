@@ -49,6 +49,8 @@ extern "C" {
     pub fn b200tfhe_keyswitch_batch(ctx: *mut b200tfhe_ctx, input: *const u64, out: *mut u64, batch: usize) -> c_int;
     pub fn b200tfhe_pbs_batch(ctx: *mut b200tfhe_ctx, input: *const u64, lut_id: *const u32, out: *mut u64, batch: usize) -> c_int;
     pub fn b200tfhe_ks_pbs_batch(ctx: *mut b200tfhe_ctx, input: *const u64, lut_id: *const u32, out: *mut u64, batch: usize) -> c_int;
+    pub fn b200tfhe_pbs_ks_batch(ctx: *mut b200tfhe_ctx, input: *const u64, lut_id: *const u32, out: *mut u64, batch: usize) -> c_int;
+    pub fn b200tfhe_pbs_ks_batch_device(ctx: *mut b200tfhe_ctx, d_in: *const u64, d_lut_id: *const u32, d_out: *mut u64, batch: usize) -> c_int;
     pub fn b200tfhe_keyswitch_batch_device(ctx: *mut b200tfhe_ctx, d_in: *const u64, d_out: *mut u64, batch: usize) -> c_int;
     pub fn b200tfhe_pbs_batch_device(ctx: *mut b200tfhe_ctx, d_in: *const u64, d_lut_id: *const u32, d_out: *mut u64, batch: usize) -> c_int;
     pub fn b200tfhe_ks_pbs_batch_device(ctx: *mut b200tfhe_ctx, d_in: *const u64, d_lut_id: *const u32, d_out: *mut u64, batch: usize) -> c_int;

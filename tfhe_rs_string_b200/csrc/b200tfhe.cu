@@ -40,6 +40,8 @@ struct b200tfhe_ctx {
     b200tfhe_params p{};
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host-buffer path
+    int sm_count = 148;
     std::mutex mu;
     mutable std::string err;
 
@@ -354,7 +356,11 @@ int b200tfhe_ctx_create(const b200tfhe_params *params, int device, b200tfhe_ctx 
         return 1;
     };
     if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess)
+        return bail("cudaStreamCreate failed");
+    ctx->sm_count = prop.multiProcessorCount;
     ctx->off_bsk = 0;
     ctx->off_ksk = align_up(ctx->bsk_len() / 2 * sizeof(double2), 256);  // N/2 complex per poly
     ctx->off_colsum = ctx->off_ksk + align_up(ctx->ksk_len() * sizeof(uint64_t), 256);
@@ -393,6 +399,8 @@ int b200tfhe_ctx_destroy(b200tfhe_ctx *ctx) {
     cudaFree(ctx->arena); cudaFree(ctx->d_twid); cudaFree(ctx->d_luts);
     cudaFree(ctx->d_in); cudaFree(ctx->d_small); cudaFree(ctx->d_out); cudaFree(ctx->d_lut_idx); cudaFree(ctx->d_digits);
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->s_h2d);
+    cudaStreamDestroy(ctx->s_d2h);
     delete ctx;
     return 0;
 }
@@ -520,6 +528,16 @@ int b200tfhe_ks_pbs_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const 
     return launch_pbs(ctx, ctx->d_small, d_lut_id, d_out, batch);
 }
 
+int b200tfhe_pbs_ks_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const uint32_t *d_lut_id, uint64_t *d_out, size_t batch) {
+    if (int rc = check_ready(ctx)) return rc;
+    std::lock_guard<std::mutex> l(ctx->mu);
+    if (batch == 0) return 0;
+    ARG_TRY(ctx, d_in && d_out, "null pointer");
+    if (int rc = ensure_workspace(ctx, batch)) return rc;
+    if (int rc = launch_pbs(ctx, d_in, d_lut_id, ctx->d_out, batch)) return rc;
+    return launch_ks(ctx, ctx->d_out, d_out, batch);
+}
+
 static int validate_lut_ids(b200tfhe_ctx *ctx, const uint32_t *lut_id, size_t batch) {
     if (!lut_id) return 0;
     const uint32_t n = (uint32_t)ctx->h_luts.size();
@@ -563,11 +581,58 @@ int b200tfhe_ks_pbs_batch(b200tfhe_ctx *ctx, const uint64_t *in, const uint32_t 
     ARG_TRY(ctx, in && out, "null pointer");
     if (int rc = validate_lut_ids(ctx, lut_id, batch)) return rc;
     if (int rc = ensure_workspace(ctx, batch)) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, batch * ctx->big_size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t big = ctx->big_size(), small = ctx->small_size();
+    // Pipelined over chunks of one full wave (4 ciphertexts per SM): the H2D copy of chunk c+1 and the
+    // D2H copy of chunk c-1 run on their own streams under the kernels of chunk c, so for pinned host
+    // buffers only the first upload and the last download are exposed.
+    const size_t chunk = (size_t)ctx->sm_count * 4;
+    const size_t n_chunks = (batch + chunk - 1) / chunk;
+    if (lut_id) CU_TRY(ctx, cudaMemcpyAsync(ctx->d_lut_idx, lut_id, batch * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+    std::vector<cudaEvent_t> ev_in(n_chunks), ev_done(n_chunks);
+    int rc = 0;
+    cudaEvent_t ev_start;   // everything already queued on the compute stream (earlier async work on the workspaces) first
+    CU_TRY(ctx, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    CU_TRY(ctx, cudaEventRecord(ev_start, ctx->stream));
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev_start, 0));
+    for (size_t c = 0; c < n_chunks; c++) {
+        cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
+    }
+    for (size_t c = 0; c < n_chunks && !rc; c++) {
+        const size_t b0 = c * chunk, nb = std::min(chunk, batch - b0);
+        cudaError_t e = cudaMemcpyAsync(ctx->d_in + b0 * big, in + b0 * big, nb * big * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->s_h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_in[c], ctx->s_h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev_in[c], 0);
+        if (e != cudaSuccess) { rc = fail(ctx, std::string("ks_pbs_batch (upload): ") + cudaGetErrorString(e)); break; }
+        rc = launch_ks(ctx, ctx->d_in + b0 * big, ctx->d_small + b0 * small, nb);
+        if (!rc) rc = launch_pbs(ctx, ctx->d_small + b0 * small, lut_id ? ctx->d_lut_idx + b0 : nullptr, ctx->d_out + b0 * big, nb);
+        if (rc) break;
+        e = cudaEventRecord(ev_done[c], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_d2h, ev_done[c], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + b0 * big, ctx->d_out + b0 * big, nb * big * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->s_d2h);
+        if (e != cudaSuccess) rc = fail(ctx, std::string("ks_pbs_batch (download): ") + cudaGetErrorString(e));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(ctx->stream), e3 = cudaStreamSynchronize(ctx->s_d2h);
+    for (size_t c = 0; c < n_chunks; c++) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); }
+    cudaEventDestroy(ev_start);
+    if (rc) return rc;
+    CU_TRY(ctx, e1); CU_TRY(ctx, e2); CU_TRY(ctx, e3);
+    return 0;
+}
+
+int b200tfhe_pbs_ks_batch(b200tfhe_ctx *ctx, const uint64_t *in, const uint32_t *lut_id, uint64_t *out, size_t batch) {
+    if (int rc = check_ready(ctx)) return rc;
+    std::lock_guard<std::mutex> l(ctx->mu);
+    if (batch == 0) return 0;
+    ARG_TRY(ctx, in && out, "null pointer");
+    if (int rc = validate_lut_ids(ctx, lut_id, batch)) return rc;
+    if (int rc = ensure_workspace(ctx, batch)) return rc;
+    const size_t small_bytes = batch * ctx->small_size() * sizeof(uint64_t);
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->d_small, in, small_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (lut_id) CU_TRY(ctx, cudaMemcpyAsync(ctx->d_lut_idx, lut_id, batch * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (int rc = launch_ks(ctx, ctx->d_in, ctx->d_small, batch)) return rc;
     if (int rc = launch_pbs(ctx, ctx->d_small, lut_id ? ctx->d_lut_idx : nullptr, ctx->d_out, batch)) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_out, batch * ctx->big_size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (int rc = launch_ks(ctx, ctx->d_out, ctx->d_small, batch)) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_small, small_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -12,8 +12,9 @@ EXPORTED_SYMBOLS = [
     "b200tfhe_ctx_create", "b200tfhe_ctx_destroy", "b200tfhe_last_error", "b200tfhe_last_global_error",
     "b200tfhe_load_ksk", "b200tfhe_load_bsk_standard", "b200tfhe_key_arena", "b200tfhe_keys_adopt",
     "b200tfhe_register_lut", "b200tfhe_register_lut_from_table",
-    "b200tfhe_keyswitch_batch", "b200tfhe_pbs_batch", "b200tfhe_ks_pbs_batch",
+    "b200tfhe_keyswitch_batch", "b200tfhe_pbs_batch", "b200tfhe_ks_pbs_batch", "b200tfhe_pbs_ks_batch",
     "b200tfhe_keyswitch_batch_device", "b200tfhe_pbs_batch_device", "b200tfhe_ks_pbs_batch_device",
+    "b200tfhe_pbs_ks_batch_device",
     "b200tfhe_lwe_linear_batch_device", "b200tfhe_sync", "b200tfhe_stream",
     "b200tfhe_set_profiling", "b200tfhe_get_kernel_times", "b200tfhe_set_pbs_variant",
     "b200tfhe_debug_negacyclic_mul",
@@ -34,6 +35,11 @@ class Params(C.Structure):
         ("ks_base_log", C.c_uint32), ("ks_level", C.c_uint32),
         ("message_modulus", C.c_uint32), ("carry_modulus", C.c_uint32),
     ]
+
+    @classmethod
+    def message_2_carry_2_pbs_ks(cls):
+        """PARAM_MESSAGE_2_CARRY_2_PBS_KS (shortint/parameters/mod.rs:1155-1169)."""
+        return cls(870, 1, 2048, 23, 1, 4, 4, 4, 4)
 
     @classmethod
     def message_2_carry_2(cls):
@@ -87,6 +93,8 @@ def load_library():
         "b200tfhe_keyswitch_batch_device": [ctx, u64p, u64p, C.c_size_t],
         "b200tfhe_pbs_batch_device": [ctx, u64p, u32p, u64p, C.c_size_t],
         "b200tfhe_ks_pbs_batch_device": [ctx, u64p, u32p, u64p, C.c_size_t],
+        "b200tfhe_pbs_ks_batch": [ctx, u64p, u32p, u64p, C.c_size_t],
+        "b200tfhe_pbs_ks_batch_device": [ctx, u64p, u32p, u64p, C.c_size_t],
         "b200tfhe_lwe_linear_batch_device": [ctx, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_size_t],
         "b200tfhe_sync": [ctx],
         "b200tfhe_stream": [ctx, C.POINTER(C.c_void_p)],
@@ -221,6 +229,17 @@ class Engine:
             ids = np.ascontiguousarray(ids, dtype=np.uint32)
         self._check(self.L.b200tfhe_ks_pbs_batch(self.h, _ptr(cts), _ptr(ids), _ptr(out), batch))
         return out
+
+    def pbs_ks_batch(self, small_cts, lut_ids=None):
+        """apply_lookup_table for PBSOrder::BootstrapKeyswitch over a batch of small-key ciphertexts."""
+        cts = np.ascontiguousarray(small_cts, dtype=np.uint64).reshape(-1, self.params.small_lwe_size)
+        ids = None if lut_ids is None else np.ascontiguousarray(lut_ids, dtype=np.uint32)
+        out = np.empty_like(cts)
+        self._check(self.L.b200tfhe_pbs_ks_batch(self.h, _ptr(cts), _ptr(ids), _ptr(out), cts.shape[0]))
+        return out
+
+    def pbs_ks_batch_device(self, d_in, d_lut_ids, d_out, batch):
+        self._check(self.L.b200tfhe_pbs_ks_batch_device(self.h, _ptr(d_in), _ptr(d_lut_ids), _ptr(d_out), batch))
 
     # ---- device-buffer hot path (torch CUDA tensors or raw device addresses)
     def keyswitch_batch_device(self, d_in, d_out, batch):
