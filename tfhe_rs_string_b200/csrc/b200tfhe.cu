@@ -16,6 +16,7 @@
 #include "ks_mma.cuh"
 #include "pbs_kernel.cuh"
 #include "pbs_kernel3.cuh"
+#include "pbs_kernel_lat.cuh"
 #include "programs.hpp"
 
 using namespace b200;
@@ -257,6 +258,18 @@ int launch_pbs3_cts(b200tfhe_ctx *ctx, const PbsArgs &a) {
     return 0;
 }
 
+template <int CTS>
+int launch_pbs_lat(b200tfhe_ctx *ctx, const PbsArgs &a) {
+    static bool configured[16] = {};
+    constexpr size_t smem = pbs_lat_smem_bytes<CTS>();
+    if (!configured[ctx->device & 15]) {
+        CU_TRY(ctx, cudaFuncSetAttribute(pbs_lat_kernel<CTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[ctx->device & 15] = true;
+    }
+    pbs_lat_kernel<CTS><<<(unsigned)((a.batch + CTS - 1) / CTS), 256, smem, ctx->stream>>>(a);
+    return 0;
+}
+
 // Ciphertexts per CTA: the fewest that still fit the batch into the minimum number of waves over the
 // SMs (one CTA per SM).  Large batches get 4 (throughput); a dependency level with few bootstraps
 // gets 1-3, which shortens every CMUX step (fewer warps share an SM sub-partition) and so the
@@ -266,6 +279,10 @@ int launch_pbs3(b200tfhe_ctx *ctx, const PbsArgs &a) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const long long waves = (a.batch + 4LL * sms - 1) / (4LL * sms);
     const long long per_cta = (a.batch + waves * sms - 1) / (waves * sms);
+    // one or two ciphertexts per SM: the latency kernel (two warps per polynomial, pbs_kernel_lat.cuh)
+    static const int dev_lat = getenv("B200TFHE_PBS_LAT") ? atoi(getenv("B200TFHE_PBS_LAT")) : 1;  // development knob
+    if (dev_lat && per_cta == 1) return launch_pbs_lat<1>(ctx, a);
+    if (dev_lat && per_cta == 2) return launch_pbs_lat<2>(ctx, a);
     switch ((int)per_cta) {
         case 1: return launch_pbs3_cts<1>(ctx, a);
         case 2: return launch_pbs3_cts<2>(ctx, a);

@@ -1,0 +1,396 @@
+// pbs_kernel_lat.cuh -- latency variant of the programmable bootstrap for small batches (same contract
+// and reference citations as pbs_kernel.cuh / pbs_kernel3.cuh).
+//
+// A CMUX step is a serial dependency chain per polynomial; with one warp per polynomial that chain
+// is 14 k cycles.  Here a polynomial gets TWO warps (warps q and q + 4, same TMEM quadrant q): thread
+// (lane l, half h) owns the 16 folded points l + 32 m, m in [16 h, 16 h + 16).  The 32-point passes of
+// the 32 x 32 FFT become a cross-warp radix-2 stage plus a 16-point transform in registers:
+//   forward (DIF first):  t = own + s * recv (s = +1 / -1 for h = 0 / 1); h = 1 multiplies by -W32^mm;
+//                         16-point DIT -> outputs with index 2 kappa + h
+//   inverse (DIT last):   16-point DIT on the inputs with index 2 kappa + h; h = 1 multiplies by
+//                         conj(W32^mm); out = recv + s * own
+// The 16 values cross between the two warps through TMEM (lane private: thread (l, 0) <-> (l, 1)), the
+// lane <-> register transposition between the passes stays in shared memory (shared by the two
+// warps).  Frequency layout is unchanged: thread (lane k1, h) holds F[k1 + 32 (2 kappa + h)], so the
+// Fourier BSK produced by bsk_to_fourier_kernel is used as is.  tools/proto_fft16x2.py is the numpy
+// model of this data flow.
+//
+// Mapping: 8 warps per CTA, quadrant q = warp & 3 hosts one polynomial: ciphertext q >> 1, polynomial
+// q & 1, half h = warp >> 2; 1 or 2 ciphertexts per CTA (quadrants 2, 3 idle for 1).
+#pragma once
+#include "pbs_kernel3.cuh"
+
+namespace b200 {
+
+constexpr uint32_t kLatAcc = 128, kLatX = 256;   // TMEM columns: [0,128) twiddles (64 per half), acc + 64 h, exchange + 64 h
+__host__ __device__ constexpr int brev4(int x) { return ((x & 1) << 3) | ((x & 2) << 1) | ((x & 4) >> 1) | ((x & 8) >> 3); }
+
+// In-register 16-point DFT, decimation in time: input in bit-reversed register order, output natural.
+template <bool INV>
+__device__ __forceinline__ void fft16_dit(double (&xr)[16], double (&xi)[16]) {
+#pragma unroll
+    for (int half = 1; half < 16; half <<= 1) {
+#pragma unroll
+        for (int base = 0; base < 16; base += 2 * half) {
+#pragma unroll
+            for (int t = 0; t < half; t++)
+                bfly<INV>(xr[base + t], xi[base + t], xr[base + t + half], xi[base + t + half], t * (16 / half));   // W16^(t*8/half) = W32^(t*16/half)
+        }
+    }
+}
+
+__device__ __forceinline__ void pair_barrier(const int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void quad_barrier(const int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// send 16 complex values to the sibling warp (64 TMEM columns at xout), receive its 16 (xin)
+__device__ __forceinline__ void lat_send(const double (&vr)[16], const double (&vi)[16], const uint32_t xout) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t s[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            undbl(vr[4 * k + j], s[4 * j], s[4 * j + 1]);
+            undbl(vi[4 * k + j], s[4 * j + 2], s[4 * j + 3]);
+        }
+        tmem_st16_nc(xout + k * 16, s);
+    }
+    tmem_wait_st();
+    tmem_fence_before();
+}
+__device__ __forceinline__ void lat_recv(double (&vr)[16], double (&vi)[16], const uint32_t xin) {
+    tmem_fence_after();
+    uint32_t g0[16], g1[16];
+    tmem_ld16_nc(xin, g0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t(&g)[16] = (k & 1) ? g1 : g0;
+        tmem_wait_ld16(g);
+        if (k < 3) tmem_ld16_nc(xin + (k + 1) * 16, (k & 1) ? g0 : g1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            vr[4 * k + j] = dbl(g[4 * j], g[4 * j + 1]);
+            vi[4 * k + j] = dbl(g[4 * j + 2], g[4 * j + 3]);
+        }
+    }
+}
+
+// forward cross-warp stage + 16-point transform: x natural (own half) -> y[kappa] = output 2 kappa + h
+__device__ __forceinline__ void lat_fwd_pass(const double (&xr)[16], const double (&xi)[16], double (&yr)[16], double (&yi)[16],
+                                             const int h, const double sgn, const uint32_t xout, const uint32_t xin, const int bar) {
+    lat_send(xr, xi, xout);
+    pair_barrier(bar);
+    double rr[16], ri[16];
+    lat_recv(rr, ri, xin);
+#pragma unroll
+    for (int mm = 0; mm < 16; mm++) {
+        double tr = fma(sgn, rr[mm], xr[mm]), ti = fma(sgn, ri[mm], xi[mm]);
+        if (h && mm) {   // times -W32^mm (warp-uniform branch)
+            const double wr = -c_w32[mm].x, wi = -c_w32[mm].y;
+            const double nr = fma(-ti, wi, tr * wr);
+            ti = fma(ti, wr, tr * wi);
+            tr = nr;
+        } else if (h) {
+            tr = -tr; ti = -ti;
+        }
+        yr[brev4(mm)] = tr; yi[brev4(mm)] = ti;
+    }
+    fft16_dit<false>(yr, yi);
+}
+// inverse: x[brev4(kappa)] = inputs 2 kappa + h -> y[mm] = result for index mm + 16 h
+__device__ __forceinline__ void lat_inv_pass(double (&xr)[16], double (&xi)[16], double (&yr)[16], double (&yi)[16],
+                                             const int h, const double sgn, const uint32_t xout, const uint32_t xin, const int bar) {
+    fft16_dit<true>(xr, xi);
+    if (h) {
+#pragma unroll
+        for (int mm = 1; mm < 16; mm++) {   // times conj(W32^mm)
+            const double wr = c_w32[mm].x, wi = -c_w32[mm].y;
+            const double nr = fma(-xi[mm], wi, xr[mm] * wr);
+            xi[mm] = fma(xi[mm], wr, xr[mm] * wi);
+            xr[mm] = nr;
+        }
+    }
+    lat_send(xr, xi, xout);
+    pair_barrier(bar);
+    lat_recv(yr, yi, xin);
+#pragma unroll
+    for (int mm = 0; mm < 16; mm++) {
+        yr[mm] = fma(sgn, xr[mm], yr[mm]);
+        yi[mm] = fma(sgn, xi[mm], yi[mm]);
+    }
+}
+
+template <int CTS>
+__host__ __device__ constexpr size_t pbs_lat_smem_bytes() {
+    return kPbsHeaderBytes + kBskSliceBytes + (size_t)CTS * pbs_ct_smem_bytes();
+}
+
+template <int CTS>
+__global__ void __launch_bounds__(256, 1) pbs_lat_kernel(const PbsArgs a) {
+    static_assert(CTS == 1 || CTS == 2, "1 or 2 ciphertexts per CTA");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qd = warp & 3, h = warp >> 2;
+    const int ctl = qd >> 1, p = qd & 1;
+    const int ct = blockIdx.x * CTS + ctl;
+    const bool active = ctl < CTS && ct < a.batch;
+    const double sgn = h ? -1.0 : 1.0;
+
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem);
+    uint64_t *bsk_bar = reinterpret_cast<uint64_t *>(smem + 8);
+    unsigned int *consumed = reinterpret_cast<unsigned int *>(smem + 16);
+    double2 *bsk_s = reinterpret_cast<double2 *>(smem + kPbsHeaderBytes);
+    unsigned char *ctbase = smem + kPbsHeaderBytes + kBskSliceBytes + (size_t)(ctl < CTS ? ctl : 0) * pbs_ct_smem_bytes();
+    double2 *tb_own = reinterpret_cast<double2 *>(ctbase) + p * kTBufElems;            // shared by the two warps of the polynomial
+    const double2 *tb_oth = reinterpret_cast<double2 *>(ctbase) + (1 - p) * kTBufElems;
+    uint16_t *ahat = reinterpret_cast<uint16_t *>(ctbase + (size_t)2 * kTBufElems * sizeof(double2));
+    uint64_t *rot = reinterpret_cast<uint64_t *>(tb_own);   // rotation copy (r = -acc) aliases the transposition buffer
+
+    if (warp == 0) tmem_alloc(slot, 512);
+    if (threadIdx.x == 0) {
+        mbar_init(bsk_bar, 1);
+        *consumed = 0;
+    }
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t tbase = *slot;
+    const uint32_t tquad = tbase + (((uint32_t)qd * 32u) << 16);
+    const uint32_t t_tw = tquad + (uint32_t)h * 64u;
+    const uint32_t t_acc = tquad + kLatAcc + (uint32_t)h * 64u;
+    const uint32_t t_x_own = tquad + kLatX + (uint32_t)h * 64u, t_x_oth = tquad + kLatX + (uint32_t)(1 - h) * 64u;
+    const int bar_pair = 1 + qd, bar_ct = 5 + ctl;
+    if (active) {   // this warp's 16 inter-pass twiddles T'[2 kappa + h][lane]
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t r[16];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const double2 t = __ldg(a.twid + (2 * (4 * c + kk) + h) * 32 + lane);
+                undbl(t.x, r[4 * kk], r[4 * kk + 1]);
+                undbl(t.y, r[4 * kk + 2], r[4 * kk + 3]);
+            }
+            tmem_st16(t_tw + c * 16, r);
+        }
+        tmem_wait_st();
+    }
+    const int n_act_cts = min(CTS, a.batch - (int)blockIdx.x * CTS);
+    const unsigned int n_act_warps = 4u * (unsigned int)n_act_cts;
+    if (threadIdx.x == 0) issue_bsk_slice(bsk_s, a.bsk, 0, bsk_bar);
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+
+    if (active) {
+        // ---------------------------------------------------------------- prologue
+        const uint64_t *lwe = a.lwe_small + (size_t)ct * (a.n + 1);
+        for (int i = (p * 2 + h) * 32 + lane; i < a.n; i += 128) ahat[i] = (uint16_t)modswitch2048(lwe[i]);
+        const uint32_t bhat = modswitch2048(lwe[a.n]);
+        const uint64_t *lut = a.luts + ((size_t)(a.lut_idx ? a.lut_idx[ct] : 0u) * 2 + p) * kN;
+        // acc = LUT * X^-b~ (polynomial_algorithms.rs:315-354); TMEM holds G = C - acc, shared memory r = -acc
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t hh[16];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int j = lane + 32 * (16 * h + 4 * c + k);
+                const uint32_t i0 = (uint32_t)(j + bhat) & 4095u, i1 = (i0 + 1024u) & 4095u;
+                uint64_t v0 = lut[i0 & 2047u], v1 = lut[i1 & 2047u];
+                if (i0 & 2048u) v0 = 0 - v0;
+                if (i1 & 2048u) v1 = 0 - v1;
+                rot[j] = 0 - v0; rot[j + kHalf] = 0 - v1;
+                const uint64_t g0 = kAccC - v0, g1 = kAccC - v1;
+                hh[4 * k] = (uint32_t)g0; hh[4 * k + 1] = (uint32_t)(g0 >> 32);
+                hh[4 * k + 2] = (uint32_t)g1; hh[4 * k + 3] = (uint32_t)(g1 >> 32);
+            }
+            tmem_st16(t_acc + c * 16, hh);
+        }
+        tmem_wait_st();
+        quad_barrier(bar_ct);   // a~ table and both rotation copies complete
+
+        // ---------------------------------------------------------------- CMUX loop
+        for (int i = 0; i < a.n; i++) {
+            double xr[16], xi[16];
+            // phase A: ct1 = acc * X^a~ - acc, round + digit, exact int -> double, twist by C_m (see pbs_kernel3.cuh)
+            {
+                const uint32_t ah = ahat[i];
+                const uint32_t base0 = (uint32_t)(lane + 512 * h + 4096 - (int)ah) & 4095u;   // source index of coefficient lane + 32*16h
+                const uint32_t base1 = (base0 + 1024u) & 4095u;
+                const uint32_t pos0 = base0 & 2047u, pos1 = base1 & 2047u;
+                const uint32_t tn0 = (base0 & 2048u) ? 0u : 0xFFFFFFFFu, tn1 = (base1 & 2048u) ? 0u : 0xFFFFFFFFu;
+                const int mc0 = (int)((2048u - pos0 + 31u) >> 5), mc1 = (int)((2048u - pos1 + 31u) >> 5);
+                const uint64_t *pn0 = rot + pos0, *pn1 = rot + pos1;
+                uint32_t h0[16], h1[16];
+                tmem_ld16_nc(t_acc, h0);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t(&hh)[16] = (c & 1) ? h1 : h0;
+                    tmem_wait_ld16(hh);
+                    if (c < 3) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int mm = 4 * c + k;
+                        const bool w0 = mm >= mc0, w1 = mm >= mc1;
+                        const uint64_t r0 = (w0 ? pn0 - kN : pn0)[32 * mm], r1 = (w1 ? pn1 - kN : pn1)[32 * mm];
+                        const uint32_t t0 = w0 ? ~tn0 : tn0, t1 = w1 ? ~tn1 : tn1;
+                        const uint64_t T0 = pack64(t0, t0), T1 = pack64(t1, t1);
+                        const uint64_t e0 = pack64(hh[4 * k], hh[4 * k + 1]) + (r0 ^ T0) - T0;
+                        const uint64_t e1 = pack64(hh[4 * k + 2], hh[4 * k + 3]) + (r1 ^ T1) - T1;
+                        const double fr = dbl((uint32_t)(e0 >> 41), 0x43300000u) - 4503599631564799.0;
+                        const double fi = dbl((uint32_t)(e1 >> 41), 0x43300000u) - 4503599631564799.0;
+                        const double2 cm = c_twm[16 * h + mm];
+                        xr[mm] = fma(-fi, cm.y, fr * cm.x);
+                        xi[mm] = fma(fi, cm.x, fr * cm.y);
+                    }
+                }
+            }
+            // (the barrier inside the first pass also orders both warps' rotation reads before the buffer is reused)
+
+            // ---- forward transform
+            double yr[16], yi[16];
+            lat_fwd_pass(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);
+            {
+                uint32_t t0[16], t1[16];
+                tmem_ld16_nc(t_tw, t0);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t(&t)[16] = (c & 1) ? t1 : t0;
+                    tmem_wait_ld16(t);
+                    if (c < 3) tmem_ld16_nc(t_tw + (c + 1) * 16, (c & 1) ? t0 : t1);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const int kap = 4 * c + kk;
+                        double2 y;
+                        cmul_tw<false>(y.x, y.y, yr[kap], yi[kap], t, kk);
+                        tb_own[lane * kTStride + 2 * kap + h] = y;
+                    }
+                }
+            }
+            pair_barrier(bar_pair);
+#pragma unroll
+            for (int ll = 0; ll < 16; ll++) {
+                const double2 v = tb_own[(ll + 16 * h) * kTStride + lane];
+                xr[ll] = v.x; xi[ll] = v.y;
+            }
+            lat_fwd_pass(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier also orders the transposition reads before the writes below
+
+            // ---- exchange the transforms between the two polynomials, Out_p = B[p][p] F_p + B[1-p][p] F_{1-p}
+#pragma unroll
+            for (int kap = 0; kap < 16; kap++) tb_own[(2 * kap + h) * 32 + lane] = make_double2(yr[kap], yi[kap]);
+            mbar_wait(bsk_bar, (uint32_t)(i & 1));
+            double zr[16], zi[16];
+            {
+                const double2 *b_own = bsk_s + (size_t)(p * 2 + p) * kHalf + lane;
+#pragma unroll
+                for (int kap = 0; kap < 16; kap++) {
+                    const double2 bo = b_own[(2 * kap + h) * 32];
+                    zr[brev4(kap)] = fma(-bo.y, yi[kap], bo.x * yr[kap]);
+                    zi[brev4(kap)] = fma(bo.y, yr[kap], bo.x * yi[kap]);
+                }
+            }
+            quad_barrier(bar_ct);
+            {
+                const double2 *b_oth = bsk_s + (size_t)((1 - p) * 2 + p) * kHalf + lane;
+#pragma unroll
+                for (int kap = 0; kap < 16; kap++) {
+                    const int q = 2 * kap + h;
+                    const double2 bx = b_oth[q * 32], g = tb_oth[q * 32 + lane];
+                    const double o_r = fma(bx.x, g.x, zr[brev4(kap)]), o_i = fma(bx.x, g.y, zi[brev4(kap)]);
+                    zr[brev4(kap)] = fma(-bx.y, g.y, o_r); zi[brev4(kap)] = fma(bx.y, g.x, o_i);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {   // this warp is done with the slice; the last of the CTA's warps refills the buffer
+                const unsigned int old = atomicAdd(consumed, 1u);
+                if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
+                    issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
+            }
+            quad_barrier(bar_ct);   // the sibling polynomial has read this one's transform before the buffer is reused
+
+            // ---- inverse transform
+            lat_inv_pass(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // y[ll]: index l = ll + 16 h of lane k1
+#pragma unroll
+            for (int ll = 0; ll < 16; ll++) tb_own[lane * kTStride + ll + 16 * h] = make_double2(yr[ll], yi[ll]);
+            pair_barrier(bar_pair);
+            {
+                uint32_t t0[16], t1[16];
+                tmem_ld16_nc(t_tw, t0);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t(&t)[16] = (c & 1) ? t1 : t0;
+                    tmem_wait_ld16(t);
+                    if (c < 3) tmem_ld16_nc(t_tw + (c + 1) * 16, (c & 1) ? t0 : t1);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const int kap = 4 * c + kk;
+                        const double2 v = tb_own[(2 * kap + h) * kTStride + lane];
+                        cmul_tw<true>(zr[brev4(kap)], zi[brev4(kap)], v.x, v.y, t, kk);
+                    }
+                }
+            }
+            lat_inv_pass(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier orders the transposition reads before the rotation copy below
+
+            // ---- phase D: untwist, from_torus, G -= delta, refresh both copies
+            uint64_t dl0[16], dl1[16];
+#pragma unroll
+            for (int mm = 0; mm < 16; mm++) {
+                const double2 cm = c_twm[16 * h + mm];
+                const double ur = fma(yi[mm], cm.y, yr[mm] * cm.x);
+                const double ui = fma(yi[mm], cm.x, -(yr[mm] * cm.y));
+                dl0[mm] = from_torus_exp(ur); dl1[mm] = from_torus_exp(ui);
+            }
+            {
+                uint32_t h0[16], h1[16];
+                tmem_ld16_nc(t_acc, h0);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t(&hh)[16] = (c & 1) ? h1 : h0;
+                    tmem_wait_ld16(hh);
+                    if (c < 3) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int mm = 4 * c + k;
+                        const int j = lane + 32 * (mm + 16 * h);
+                        const uint64_t g0 = pack64(hh[4 * k], hh[4 * k + 1]) - dl0[mm];
+                        const uint64_t g1 = pack64(hh[4 * k + 2], hh[4 * k + 3]) - dl1[mm];
+                        rot[j] = g0 - kAccC; rot[j + kHalf] = g1 - kAccC;
+                        hh[4 * k] = (uint32_t)g0; hh[4 * k + 1] = (uint32_t)(g0 >> 32);
+                        hh[4 * k + 2] = (uint32_t)g1; hh[4 * k + 3] = (uint32_t)(g1 >> 32);
+                    }
+                    tmem_st16_nc(t_acc + c * 16, hh);
+                }
+                tmem_wait_st();
+            }
+            pair_barrier(bar_pair);   // rotation copy complete (both halves) before the next step's gather
+        }
+
+        // ---------------------------------------------------------------- sample extraction
+        uint64_t *o = a.out + (size_t)ct * (kN + 1);
+        if (p == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t hh[16];
+                tmem_ld16(t_acc + c * 16, hh);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int j = lane + 32 * (16 * h + 4 * c + k);
+                    const uint64_t a0 = kAccC - pack64(hh[4 * k], hh[4 * k + 1]);
+                    const uint64_t a1 = kAccC - pack64(hh[4 * k + 2], hh[4 * k + 3]);
+                    if (j == 0) o[0] = a0; else o[kN - j] = 0 - a0;
+                    o[kHalf - j] = 0 - a1;
+                }
+            }
+        } else if (h == 0) {
+            uint32_t hh[16];
+            tmem_ld16(t_acc, hh);
+            tmem_wait_ld();
+            if (lane == 0) o[kN] = kAccC - pack64(hh[0], hh[1]);
+        }
+    }
+
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace b200
