@@ -266,7 +266,7 @@ int launch_pbs_lat(b200tfhe_ctx *ctx, const PbsArgs &a) {
         CU_TRY(ctx, cudaFuncSetAttribute(pbs_lat_kernel<CTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[ctx->device & 15] = true;
     }
-    pbs_lat_kernel<CTS><<<(unsigned)((a.batch + CTS - 1) / CTS), 256, smem, ctx->stream>>>(a);
+    pbs_lat_kernel<CTS><<<(unsigned)((a.batch + CTS - 1) / CTS), CTS == 4 ? 512 : 256, smem, ctx->stream>>>(a);
     return 0;
 }
 
@@ -283,6 +283,7 @@ int launch_pbs3(b200tfhe_ctx *ctx, const PbsArgs &a) {
     static const int dev_lat = getenv("B200TFHE_PBS_LAT") ? atoi(getenv("B200TFHE_PBS_LAT")) : 1;  // development knob
     if (dev_lat && per_cta == 1) return launch_pbs_lat<1>(ctx, a);
     if (dev_lat && per_cta == 2) return launch_pbs_lat<2>(ctx, a);
+    if (dev_lat >= 2 && per_cta == 4) return launch_pbs_lat<4>(ctx, a);   // experiment: 16-warp throughput configuration
     switch ((int)per_cta) {
         case 1: return launch_pbs3_cts<1>(ctx, a);
         case 2: return launch_pbs3_cts<2>(ctx, a);

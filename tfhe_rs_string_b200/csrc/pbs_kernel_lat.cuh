@@ -74,13 +74,60 @@ __device__ __forceinline__ void lat_recv(double (&vr)[16], double (&vi)[16], con
     }
 }
 
+// Two-round exchange for the 16-warp configuration, where only 32 TMEM columns per warp are left: 8
+// values per round; round B writes into the buffer this warp has just read (the sibling does the
+// same), so no write-after-read barrier is needed between the rounds.
+__device__ __forceinline__ void lat_put8(const double (&vr)[16], const double (&vi)[16], const int off, const uint32_t x) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        uint32_t s[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            undbl(vr[off + 4 * k + j], s[4 * j], s[4 * j + 1]);
+            undbl(vi[off + 4 * k + j], s[4 * j + 2], s[4 * j + 3]);
+        }
+        tmem_st16_nc(x + k * 16, s);
+    }
+    tmem_wait_st();
+    tmem_fence_before();
+}
+__device__ __forceinline__ void lat_get8(double (&vr)[16], double (&vi)[16], const int off, const uint32_t x) {
+    tmem_fence_after();
+    uint32_t g0[16], g1[16];
+    tmem_ld16_nc(x, g0);
+    tmem_ld16_nc(x + 16, g1);
+    tmem_wait_ld16(g0);
+    tmem_wait_ld16(g1);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        vr[off + j] = dbl(g0[4 * j], g0[4 * j + 1]); vi[off + j] = dbl(g0[4 * j + 2], g0[4 * j + 3]);
+        vr[off + 4 + j] = dbl(g1[4 * j], g1[4 * j + 1]); vi[off + 4 + j] = dbl(g1[4 * j + 2], g1[4 * j + 3]);
+    }
+}
+// swap 16 complex values with the sibling warp: send v, receive r
+template <bool TWO_ROUNDS>
+__device__ __forceinline__ void lat_swap(const double (&vr)[16], const double (&vi)[16], double (&rr)[16], double (&ri)[16],
+                                         const uint32_t xout, const uint32_t xin, const int bar) {
+    if (!TWO_ROUNDS) {
+        lat_send(vr, vi, xout);
+        pair_barrier(bar);
+        lat_recv(rr, ri, xin);
+    } else {
+        lat_put8(vr, vi, 0, xout);
+        pair_barrier(bar);
+        lat_get8(rr, ri, 0, xin);
+        lat_put8(vr, vi, 8, xin);     // the buffer just read; the sibling fills xout
+        pair_barrier(bar);
+        lat_get8(rr, ri, 8, xout);
+    }
+}
+
 // forward cross-warp stage + 16-point transform: x natural (own half) -> y[kappa] = output 2 kappa + h
+template <bool TWO_ROUNDS>
 __device__ __forceinline__ void lat_fwd_pass(const double (&xr)[16], const double (&xi)[16], double (&yr)[16], double (&yi)[16],
                                              const int h, const double sgn, const uint32_t xout, const uint32_t xin, const int bar) {
-    lat_send(xr, xi, xout);
-    pair_barrier(bar);
     double rr[16], ri[16];
-    lat_recv(rr, ri, xin);
+    lat_swap<TWO_ROUNDS>(xr, xi, rr, ri, xout, xin, bar);
 #pragma unroll
     for (int mm = 0; mm < 16; mm++) {
         double tr = fma(sgn, rr[mm], xr[mm]), ti = fma(sgn, ri[mm], xi[mm]);
@@ -97,6 +144,7 @@ __device__ __forceinline__ void lat_fwd_pass(const double (&xr)[16], const doubl
     fft16_dit<false>(yr, yi);
 }
 // inverse: x[brev4(kappa)] = inputs 2 kappa + h -> y[mm] = result for index mm + 16 h
+template <bool TWO_ROUNDS>
 __device__ __forceinline__ void lat_inv_pass(double (&xr)[16], double (&xi)[16], double (&yr)[16], double (&yi)[16],
                                              const int h, const double sgn, const uint32_t xout, const uint32_t xin, const int bar) {
     fft16_dit<true>(xr, xi);
@@ -109,9 +157,7 @@ __device__ __forceinline__ void lat_inv_pass(double (&xr)[16], double (&xi)[16],
             xr[mm] = nr;
         }
     }
-    lat_send(xr, xi, xout);
-    pair_barrier(bar);
-    lat_recv(yr, yi, xin);
+    lat_swap<TWO_ROUNDS>(xr, xi, yr, yi, xout, xin, bar);
 #pragma unroll
     for (int mm = 0; mm < 16; mm++) {
         yr[mm] = fma(sgn, xr[mm], yr[mm]);
@@ -124,13 +170,16 @@ __host__ __device__ constexpr size_t pbs_lat_smem_bytes() {
     return kPbsHeaderBytes + kBskSliceBytes + (size_t)CTS * pbs_ct_smem_bytes();
 }
 
+// CTS = 1, 2: 8 warps (latency); CTS = 4: 16 warps, 128 registers per thread, two polynomial pairs per
+// TMEM quadrant (ciphertexts c and c + 2 share the sub-partitions), two-round exchanges (throughput).
 template <int CTS>
-__global__ void __launch_bounds__(256, 1) pbs_lat_kernel(const PbsArgs a) {
-    static_assert(CTS == 1 || CTS == 2, "1 or 2 ciphertexts per CTA");
+__global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const PbsArgs a) {
+    static_assert(CTS == 1 || CTS == 2 || CTS == 4, "1, 2 or 4 ciphertexts per CTA");
+    constexpr bool kTwoRounds = CTS == 4;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qd = warp & 3, h = warp >> 2;
-    const int ctl = qd >> 1, p = qd & 1;
+    const int qd = warp & 3, h = (warp >> 2) & 1, pr = warp >> 3;
+    const int ctl = 2 * pr + (qd >> 1), p = qd & 1;
     const int ct = blockIdx.x * CTS + ctl;
     const bool active = ctl < CTS && ct < a.batch;
     const double sgn = h ? -1.0 : 1.0;
@@ -156,10 +205,11 @@ __global__ void __launch_bounds__(256, 1) pbs_lat_kernel(const PbsArgs a) {
     const uint32_t tbase = *slot;
     const uint32_t tquad = tbase + (((uint32_t)qd * 32u) << 16);
     const uint32_t t_tw = tquad + (uint32_t)h * 64u;
-    const uint32_t t_acc = tquad + kLatAcc + (uint32_t)h * 64u;
-    const uint32_t t_x_own = tquad + kLatX + (uint32_t)h * 64u, t_x_oth = tquad + kLatX + (uint32_t)(1 - h) * 64u;
-    const int bar_pair = 1 + qd, bar_ct = 5 + ctl;
-    if (active) {   // this warp's 16 inter-pass twiddles T'[2 kappa + h][lane]
+    const uint32_t t_acc = tquad + kLatAcc + (uint32_t)(pr * 2 + h) * 64u;
+    const uint32_t t_x_own = kTwoRounds ? tquad + 384u + (uint32_t)(pr * 2 + h) * 32u : tquad + kLatX + (uint32_t)h * 64u;
+    const uint32_t t_x_oth = kTwoRounds ? tquad + 384u + (uint32_t)(pr * 2 + 1 - h) * 32u : tquad + kLatX + (uint32_t)(1 - h) * 64u;
+    const int bar_pair = 1 + qd + 4 * pr, bar_ct = 9 + ctl;
+    if (pr == 0) {   // the quadrant's inter-pass twiddles T'[2 kappa + h][lane], one table per half
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             uint32_t r[16];
@@ -247,7 +297,7 @@ __global__ void __launch_bounds__(256, 1) pbs_lat_kernel(const PbsArgs a) {
 
             // ---- forward transform
             double yr[16], yi[16];
-            lat_fwd_pass(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);
+            lat_fwd_pass<kTwoRounds>(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);
             {
                 uint32_t t0[16], t1[16];
                 tmem_ld16_nc(t_tw, t0);
@@ -271,7 +321,7 @@ __global__ void __launch_bounds__(256, 1) pbs_lat_kernel(const PbsArgs a) {
                 const double2 v = tb_own[(ll + 16 * h) * kTStride + lane];
                 xr[ll] = v.x; xi[ll] = v.y;
             }
-            lat_fwd_pass(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier also orders the transposition reads before the writes below
+            lat_fwd_pass<kTwoRounds>(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier also orders the transposition reads before the writes below
 
             // ---- exchange the transforms between the two polynomials, Out_p = B[p][p] F_p + B[1-p][p] F_{1-p}
 #pragma unroll
@@ -307,7 +357,7 @@ __global__ void __launch_bounds__(256, 1) pbs_lat_kernel(const PbsArgs a) {
             quad_barrier(bar_ct);   // the sibling polynomial has read this one's transform before the buffer is reused
 
             // ---- inverse transform
-            lat_inv_pass(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // y[ll]: index l = ll + 16 h of lane k1
+            lat_inv_pass<kTwoRounds>(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // y[ll]: index l = ll + 16 h of lane k1
 #pragma unroll
             for (int ll = 0; ll < 16; ll++) tb_own[lane * kTStride + ll + 16 * h] = make_double2(yr[ll], yi[ll]);
             pair_barrier(bar_pair);
@@ -327,7 +377,7 @@ __global__ void __launch_bounds__(256, 1) pbs_lat_kernel(const PbsArgs a) {
                     }
                 }
             }
-            lat_inv_pass(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier orders the transposition reads before the rotation copy below
+            lat_inv_pass<kTwoRounds>(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier orders the transposition reads before the rotation copy below
 
             // ---- phase D: untwist, from_torus, G -= delta, refresh both copies
             uint64_t dl0[16], dl1[16];
