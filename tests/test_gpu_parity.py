@@ -93,6 +93,17 @@ def test_pbs_parity(engine, real_keys, variant):
         engine.set_pbs_variant(3)
 
 
+@pytest.mark.parametrize("batch", [1, 2, 149, 297, 445, 593])
+def test_ks_pbs_every_launch_configuration(engine, real_keys, batch):
+    """The PBS launcher picks the kernel by batch size (latency kernel with 1 / 2 ciphertexts per CTA,
+    pbs_kernel3 with 3 / 4, partially filled last CTA): every configuration must decrypt exactly."""
+    msgs = (np.arange(batch) * 7 + 3) % 16
+    cts = real_keys.encrypt_batch(msgs, seed=900 + batch)
+    f = lambda x: (x * 5 + 1) % 16
+    out = engine.ks_pbs_batch(cts, np.full(batch, engine.generate_lookup_table(f), dtype=np.uint32))
+    assert list(real_keys.decrypt_batch(out)) == [f(int(m)) for m in msgs]
+
+
 def test_ks_pbs_all_messages_full_batch(engine, real_keys):
     # BASELINE config[0]: 1024 ciphertexts, identity LUT, messages i mod 16 (SURVEY 8d config 1)
     B = 1024
