@@ -307,6 +307,26 @@ def run_b200(args):
             "gpu_launches": int(kt["pbs_launches"] + 2 * kt["ks_launches"]),   # per step: ks_digits + ks_mma + pbs
             "clocks": clocks,
         }
+        # second half of BASELINE.json's metric: FheString eq latency (one pair of 64-char strings, 4 blocks
+        # per char; device-resident inputs, all dependency levels on the GPU) and the batch-of-256 time
+        try:
+            lat = {}
+            for label, shape in (("one_pair_64_chars", [1, 64, 64, 4]), ("256_pairs_64_chars", [256, 64, 64, 4])):
+                prog = T.Program(eng, "string_eq", shape)
+                d_i = torch.from_numpy(rng.integers(-2**63, 2**63, (prog.info["n_inputs"], p.big_lwe_size), dtype=np.int64)).cuda()
+                d_o = torch.empty((prog.info["n_outputs"], p.big_lwe_size), dtype=torch.int64, device="cuda")
+                prog.run_device(d_i, d_o); eng.sync()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(3):
+                    prog.run_device(d_i, d_o)
+                e1.record(stream)
+                eng.sync(); torch.cuda.synchronize()
+                lat[label] = {"ms": e0.elapsed_time(e1) / 3, "n_pbs": prog.info["n_pbs"], "depth": prog.info["depth"]}
+                prog.close()
+            line["fhe_string_eq"] = lat
+        except Exception as ex:   # the headline line must not depend on this extra
+            line["fhe_string_eq"] = {"error": str(ex)}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             v, dt, ok, sample = cpu_baseline(args.cpu_sample, threads, B)
