@@ -140,8 +140,8 @@ int b200tfhe_set_pbs_variant(b200tfhe_ctx *ctx, int variant);
  * contains,find}.rs; apps/trivium/src/trivium/trivium_bool.rs:143-227).  A program is that schedule
  * compiled once for a workload shape: per level ONE lwe-linear launch + ONE ks_pbs_batch launch, all
  * intermediate blocks resident in HBM.  Names and shapes: tfhe_rs_string_b200/csrc/programs.hpp
- * ("radix_eq", "radix_add", "radix_sub", "radix_scalar_gt|lt|eq", "string_eq",
- * "string_to_uppercase", "string_contains", "string_find", "trivium").  Inputs and outputs are
+ * ("radix_eq|ne|add|sub|bitand|bitor|bitxor|shl", "radix_scalar_gt|lt|le|ge|eq",
+ * "string_eq|ne|starts_with|ends_with|to_uppercase|to_lowercase|contains|find", "trivium").  Inputs and outputs are
  * arrays of big-key LWE blocks (k*N+1 u64 each). */
 typedef struct b200tfhe_program b200tfhe_program;
 int b200tfhe_program_create(b200tfhe_ctx *ctx, const char *op, const uint64_t *shape, size_t n_shape,

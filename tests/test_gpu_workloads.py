@@ -107,3 +107,29 @@ def test_program_matches_cleartext_executor_and_errors(engine, real_keys):
         T.Program(engine, "no_such_op", [1])
     with pytest.raises(T.B200TfheError):
         T.Program(engine, "radix_eq", [1])
+
+
+def test_extra_ops_on_gpu(engine, real_keys):
+    """A sample of the remaining call sites through the GPU executor: ne, bitxor, shl, scalar ge,
+    to_lowercase, starts_with, ends_with."""
+    rng = np.random.default_rng(25)
+    n = 32
+    a = rng.integers(0, 256, n); b = rng.integers(0, 256, n); b[::2] = a[::2]
+    msgs = np.concatenate([blocks_of(a).ravel(), blocks_of(b).ravel()])
+    out, _ = run(engine, real_keys, "radix_ne", [n, 4], msgs, 670)
+    assert np.array_equal(out, (a != b).astype(U64))
+    out, _ = run(engine, real_keys, "radix_bitxor", [n, 4], msgs, 671)
+    assert np.array_equal(from_blocks(out.reshape(n, 4)), (a ^ b).astype(U64))
+    out, _ = run(engine, real_keys, "radix_shl", [n, 4, 3], blocks_of(a).ravel(), 672)
+    assert np.array_equal(from_blocks(out.reshape(n, 4)), ((a << 3) % 256).astype(U64))
+    out, _ = run(engine, real_keys, "radix_scalar_ge", [n, 4, 100], blocks_of(a).ravel(), 673)
+    assert np.array_equal(out, (a >= 100).astype(U64))
+    s = ["Hello, World Q", "tfhe-RS string", "ABCxyz 019 ~!@", "mixedCASEinput"]
+    out, _ = run(engine, real_keys, "string_to_lowercase", [4, 14, 4], chars(s).ravel(), 674)
+    assert ["".join(chr(int(v)) for v in row) for row in from_blocks(out.reshape(4, 14, 4))] == [x.lower() for x in s]
+    pats = ["Hell", "ring", "ABCx", "nput"]
+    msgs = np.concatenate([chars(s).ravel(), chars(pats).ravel()])
+    out, _ = run(engine, real_keys, "string_starts_with", [4, 14, 4, 4], msgs, 675)
+    assert list(out) == [int(x.startswith(q)) for x, q in zip(s, pats)]
+    out, _ = run(engine, real_keys, "string_ends_with", [4, 14, 4, 4], msgs, 676)
+    assert list(out) == [int(x.endswith(q)) for x, q in zip(s, pats)]

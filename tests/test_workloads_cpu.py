@@ -138,3 +138,47 @@ def test_trivium_encrypted_on_toy_parameters(toy_keys):
     out = toy_keys.decrypt_batch(O.circuit_run_encrypted(toy_keys, "trivium", [1, iv_lo, iv_hi], cts))
     by = bytes(sum(int(out[8 * i + j]) << j for j in range(8)) for i in range(8))
     assert by.hex().upper() == k["keystream_bytes_0_63_hex"][:16]
+
+
+def test_extra_radix_ops_cleartext():
+    """ne / bitand / bitor / bitxor / shl / scalar le, ge (radix_parallel/comparison.rs:39-62,
+    bitwise_op.rs, scalar_shift.rs, comparator.rs) against the clear operations."""
+    rng = np.random.default_rng(7)
+    n = 300
+    a = rng.integers(0, 256, n); b = rng.integers(0, 256, n)
+    b[::4] = a[::4]
+    inp = np.concatenate([blocks_of(a).ravel(), blocks_of(b).ravel()])
+    assert np.array_equal(O.circuit_run_cleartext("radix_ne", [n, 4], inp), (a != b).astype(np.uint64))
+    for op, f in (("radix_bitand", np.bitwise_and), ("radix_bitor", np.bitwise_or), ("radix_bitxor", np.bitwise_xor)):
+        r = O.circuit_run_cleartext(op, [n, 4], inp).reshape(n, 4)
+        assert r.max() < 4 and np.array_equal(from_blocks(r), f(a, b).astype(np.uint64)), op
+    for bits in (0, 1, 2, 3, 5, 7):
+        r = O.circuit_run_cleartext("radix_shl", [n, 4, bits], blocks_of(a).ravel()).reshape(n, 4)
+        assert np.array_equal(from_blocks(r), ((a << bits) % 256).astype(np.uint64)), bits
+    v = np.arange(256)
+    for scalar in (0, 64, 91, 255):
+        assert np.array_equal(O.circuit_run_cleartext("radix_scalar_le", [256, 4, scalar], blocks_of(v).ravel()), (v <= scalar).astype(np.uint64))
+        assert np.array_equal(O.circuit_run_cleartext("radix_scalar_ge", [256, 4, scalar], blocks_of(v).ravel()), (v >= scalar).astype(np.uint64))
+
+
+def test_extra_string_ops_cleartext():
+    """ne, to_lowercase, starts_with, ends_with (examples/fhe_strings/server_key/comparisons.rs:37-40,
+    change_case.rs:40-82, contains.rs:96-134, ends_with.rs) on unpadded strings."""
+    rng = np.random.default_rng(8)
+    n, L, P = 24, 12, 4
+    a = ["".join(chr(rng.integers(32, 127)) for _ in range(L)) for _ in range(n)]
+    b = list(a)
+    for i in range(0, n, 2):
+        q = int(rng.integers(0, L)); b[i] = b[i][:q] + chr(32 + (ord(b[i][q]) - 31) % 95) + b[i][q + 1:]
+    inp = np.concatenate([chars(a).ravel(), chars(b).ravel()])
+    assert list(O.circuit_run_cleartext("string_ne", [n, L, L, 4], inp)) == [int(x != y) for x, y in zip(a, b)]
+    low = O.circuit_run_cleartext("string_to_lowercase", [n, L, 4], chars(a).ravel()).reshape(n, L, 4)
+    assert ["".join(chr(int(v)) for v in row) for row in from_blocks(low)] == [s.lower() for s in a]
+    pats = [s[:P] if i % 3 == 0 else (s[-P:] if i % 3 == 1 else "zz" + s[:P - 2]) for i, s in enumerate(a)]
+    inp = np.concatenate([chars(a).ravel(), chars(pats).ravel()])
+    assert list(O.circuit_run_cleartext("string_starts_with", [n, L, P, 4], inp)) == [int(s.startswith(q)) for s, q in zip(a, pats)]
+    assert list(O.circuit_run_cleartext("string_ends_with", [n, L, P, 4], inp)) == [int(s.endswith(q)) for s, q in zip(a, pats)]
+    # pattern longer than the string: never a prefix / suffix of an unpadded string without zero characters
+    inp = np.concatenate([chars(pats).ravel(), chars(a).ravel()])
+    assert not O.circuit_run_cleartext("string_starts_with", [n, P, L, 4], inp).any()
+    assert not O.circuit_run_cleartext("string_ends_with", [n, P, L, 4], inp).any()

@@ -12,9 +12,15 @@ namespace b200 {
 //   radix_eq        shape {n_ints, n_blocks}            in: lhs[n_ints][n_blocks], rhs[n_ints][n_blocks]     out: n_ints booleans
 //   radix_add       shape {n_ints, n_blocks}            in: lhs, rhs                                         out: sum[n_ints][n_blocks]
 //   radix_sub       shape {n_ints, n_blocks}            in: lhs, rhs                                         out: diff[n_ints][n_blocks]
-//   radix_scalar_gt / radix_scalar_lt / radix_scalar_eq
+//   radix_ne        shape {n_ints, n_blocks}            in: lhs, rhs                                         out: n_ints booleans
+//   radix_bitand / radix_bitor / radix_bitxor
+//                   shape {n_ints, n_blocks}            in: lhs, rhs                                         out: result[n_ints][n_blocks]
+//   radix_shl       shape {n_ints, n_blocks, bits}      in: lhs                                              out: (lhs << bits)[n_ints][n_blocks]
+//   radix_scalar_gt / radix_scalar_lt / radix_scalar_le / radix_scalar_ge / radix_scalar_eq
 //                   shape {n_ints, n_blocks, scalar}    in: lhs                                              out: n_ints booleans
 //   string_eq       shape {n_str, len_a, len_b, nb}     in: a[n_str][len_a][nb], b[n_str][len_b][nb]         out: n_str booleans
+//   string_ne / string_starts_with / string_ends_with: same shape and inputs as string_eq (b is the pattern)
+//   string_to_lowercase: as string_to_uppercase
 //   string_to_uppercase shape {n_str, len, nb}          in: s[n_str][len][nb]                                out: s'[n_str][len][nb]
 //   string_contains shape {n_str, hay_len, pat_len, nb} in: hay[n_str][hay_len][nb], pat[n_str][pat_len][nb] out: n_str booleans
 //   string_find     shape {n_str, hay_len, pat_len, nb} in: hay, pat                                         out: per string: found, index[nb]
@@ -32,7 +38,8 @@ inline std::unique_ptr<Circuit> build_program(const std::string &op, const std::
         for (size_t k = 0; k < nb; k++) r[k] = c.input(base + k);
         return r;
     };
-    if (op == "radix_eq" || op == "radix_add" || op == "radix_sub") {
+    if (op == "radix_eq" || op == "radix_ne" || op == "radix_add" || op == "radix_sub" || op == "radix_bitand" ||
+        op == "radix_bitor" || op == "radix_bitxor") {
         need(2);
         const size_t n = shape[0], nb = shape[1];
         cp.reset(new Circuit(msg_mod, carry_mod, 2 * n * nb));
@@ -40,21 +47,33 @@ inline std::unique_ptr<Circuit> build_program(const std::string &op, const std::
         for (size_t i = 0; i < n; i++) {
             Radix a = radix_at(c, i * nb, nb), b = radix_at(c, (n + i) * nb, nb);
             if (op == "radix_eq") c.output(radix_eq(c, a, b));
+            else if (op == "radix_ne") c.output(radix_ne(c, a, b));
             else {
-                Radix r = op == "radix_add" ? radix_add(c, a, b) : radix_sub(c, a, b);
+                Radix r = op == "radix_add" ? radix_add(c, a, b) : op == "radix_sub" ? radix_sub(c, a, b)
+                        : radix_bitop(c, a, b, op == "radix_bitand" ? '&' : op == "radix_bitor" ? '|' : '^');
                 for (const Lin &blk : r) c.output(blk);
             }
         }
-    } else if (op == "radix_scalar_gt" || op == "radix_scalar_lt" || op == "radix_scalar_eq") {
+    } else if (op == "radix_shl") {
+        need(3);
+        const size_t n = shape[0], nb = shape[1];
+        cp.reset(new Circuit(msg_mod, carry_mod, n * nb));
+        Circuit &c = *cp;
+        for (size_t i = 0; i < n; i++)
+            for (const Lin &blk : scalar_left_shift(c, radix_at(c, i * nb, nb), (unsigned)shape[2])) c.output(blk);
+    } else if (op == "radix_scalar_gt" || op == "radix_scalar_lt" || op == "radix_scalar_eq" || op == "radix_scalar_le" ||
+               op == "radix_scalar_ge") {
         need(3);
         const size_t n = shape[0], nb = shape[1];
         cp.reset(new Circuit(msg_mod, carry_mod, n * nb));
         Circuit &c = *cp;
         for (size_t i = 0; i < n; i++) {
             Radix a = radix_at(c, i * nb, nb);
-            c.output(op == "radix_scalar_gt" ? scalar_gt(c, a, shape[2]) : op == "radix_scalar_lt" ? scalar_lt(c, a, shape[2]) : scalar_eq(c, a, shape[2]));
+            c.output(op == "radix_scalar_gt" ? scalar_gt(c, a, shape[2]) : op == "radix_scalar_lt" ? scalar_lt(c, a, shape[2])
+                     : op == "radix_scalar_le" ? scalar_le(c, a, shape[2]) : op == "radix_scalar_ge" ? scalar_ge(c, a, shape[2])
+                     : scalar_eq(c, a, shape[2]));
         }
-    } else if (op == "string_eq") {
+    } else if (op == "string_eq" || op == "string_ne" || op == "string_starts_with" || op == "string_ends_with") {
         need(4);
         const size_t n = shape[0], la = shape[1], lb = shape[2], nb = shape[3];
         cp.reset(new Circuit(msg_mod, carry_mod, n * (la + lb) * nb));
@@ -63,16 +82,18 @@ inline std::unique_ptr<Circuit> build_program(const std::string &op, const std::
             FheChars a(la), b(lb);
             for (size_t i = 0; i < la; i++) a[i] = radix_at(c, (s * la + i) * nb, nb);
             for (size_t i = 0; i < lb; i++) b[i] = radix_at(c, (n * la + s * lb + i) * nb, nb);
-            c.output(string_eq(c, a, b));
+            c.output(op == "string_eq" ? string_eq(c, a, b) : op == "string_ne" ? bool_not(c, string_eq(c, a, b))
+                     : op == "string_starts_with" ? string_starts_with(c, a, b) : string_ends_with(c, a, b));
         }
-    } else if (op == "string_to_uppercase") {
+    } else if (op == "string_to_uppercase" || op == "string_to_lowercase") {
         need(3);
         const size_t n = shape[0], len = shape[1], nb = shape[2];
         cp.reset(new Circuit(msg_mod, carry_mod, n * len * nb));
         Circuit &c = *cp;
         for (size_t s = 0; s < n; s++)
             for (size_t i = 0; i < len; i++) {
-                Radix r = to_uppercase_char(c, radix_at(c, (s * len + i) * nb, nb));
+                Radix ch = radix_at(c, (s * len + i) * nb, nb);
+                Radix r = op == "string_to_uppercase" ? to_uppercase_char(c, ch) : to_lowercase_char(c, ch);
                 for (const Lin &blk : r) c.output(blk);
             }
     } else if (op == "string_contains" || op == "string_find") {

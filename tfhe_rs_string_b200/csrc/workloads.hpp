@@ -126,6 +126,22 @@ inline Lin radix_eq(Circuit &c, const Radix &a, const Radix &b) {
     return all_true(c, cmp);
 }
 
+// ne_parallelized: radix_parallel/comparison.rs:39-62 (block `!=` flags, then any-true)
+inline Lin radix_ne(Circuit &c, const Radix &a, const Radix &b) {
+    const int lut = c.lut_bivariate([](uint64_t x, uint64_t y) { return (uint64_t)(x != y); }, c.msg_mod);
+    std::vector<Lin> cmp(a.size());
+    for (size_t i = 0; i < a.size(); i++) cmp[i] = c.pbs_bivariate(a[i], b[i], lut, c.msg_mod);
+    return any_true(c, cmp);
+}
+// bitand / bitor / bitxor_parallelized (integer/server_key/radix_parallel/bitwise_op.rs -> per block
+// shortint unchecked_bitand/bitor/bitxor, shortint/server_key/bitwise_op.rs:204-207): one bivariate PBS per block
+inline Radix radix_bitop(Circuit &c, const Radix &a, const Radix &b, char op) {
+    const int lut = c.lut_bivariate([op](uint64_t x, uint64_t y) { return op == '&' ? (x & y) : op == '|' ? (x | y) : (x ^ y); }, c.msg_mod);
+    Radix r(a.size());
+    for (size_t i = 0; i < a.size(); i++) r[i] = c.pbs_bivariate(a[i], b[i], lut, c.msg_mod);
+    return r;
+}
+
 // ---- scalar comparisons (src/integer/server_key/comparator.rs)
 constexpr uint64_t kInf = 0, kEq = 1, kSup = 2;
 inline std::vector<uint8_t> scalar_blocks_early_stop(const Circuit &c, uint64_t s) {   // BlockDecomposer::with_early_stop_at_zero
@@ -255,6 +271,12 @@ inline Radix to_uppercase_char(Circuit &c, const Radix &ch) {
     Radix delta = scalar_left_shift(c, bool_to_radix(c, flag, ch.size()), 5);   // scalar_mul_parallelized(.., 32)
     return radix_sub(c, ch, delta);
 }
+// to_lowercase_char, change_case.rs:69-82: (c > 64 & c < 91) -> c + 32 * flag
+inline Radix to_lowercase_char(Circuit &c, const Radix &ch) {
+    Lin flag = bool_and(c, scalar_gt(c, ch, 64), scalar_lt(c, ch, 91));
+    Radix delta = scalar_left_shift(c, bool_to_radix(c, flag, ch.size()), 5);
+    return radix_add(c, ch, delta);
+}
 // eq_no_init_padding for two unpadded strings (comparisons.rs:184-215); the serial `&=` fold of the
 // reference becomes one sum-of-flags tree over all character comparisons
 inline Lin string_eq(Circuit &c, const FheChars &a, const FheChars &b) {
@@ -273,6 +295,19 @@ inline Lin match_at(Circuit &c, const FheChars &hay, const FheChars &pat, size_t
     std::vector<Lin> flags;
     for (size_t j = 0; j < pat.size(); j++) flags.push_back(radix_eq(c, hay[pos + j], pat[j]));
     return all_true(c, flags);
+}
+// starts_with_encrypted_vec with Padding::None (contains.rs:96-134): the overlapping characters agree and,
+// when the prefix is longer than the string, its next character is a padding zero
+inline Lin string_starts_with(Circuit &c, const FheChars &s, const FheChars &prefix) {
+    std::vector<Lin> flags;
+    for (size_t j = 0; j < std::min(s.size(), prefix.size()); j++) flags.push_back(radix_eq(c, s[j], prefix[j]));
+    if (prefix.size() > s.size()) flags.push_back(scalar_eq(c, prefix[s.size()], 0));
+    return all_true(c, flags);
+}
+// is_suffix_of_string for two unpadded strings (pattern.rs: the pattern must match at position len - pat_len)
+inline Lin string_ends_with(Circuit &c, const FheChars &s, const FheChars &suffix) {
+    if (suffix.size() > s.size()) return c.constant(0);
+    return match_at(c, s, suffix, s.size() - suffix.size());
 }
 // contains_unpadded_string, contains.rs:77-92: OR over all start positions
 inline Lin string_contains(Circuit &c, const FheChars &hay, const FheChars &pat) {
