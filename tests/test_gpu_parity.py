@@ -190,3 +190,52 @@ def test_device_entry_points_match_host(engine, real_keys):
     engine.ks_pbs_batch_device(d_in, d_ids, d_out, B)
     engine.sync()
     assert np.array_equal(d_out.cpu().numpy().view(U64), host)   # same kernels, same order: deterministic
+
+
+def test_concurrent_callers_share_one_context(engine, real_keys):
+    """ServerKey is Sync in the reference (rayon workers call apply_lookup_table concurrently); the
+    context serialises concurrent batch calls and each caller gets its own results."""
+    import threading
+    fs = [lambda x: x, lambda x: (x + 5) % 16, lambda x: (3 * x) % 16, lambda x: 15 - x]
+    ids = [engine.generate_lookup_table(f) for f in fs]
+    results, errors = {}, []
+
+    def worker(k):
+        try:
+            msgs = (np.arange(37 + 11 * k) + k) % 16
+            cts = real_keys.encrypt_batch(msgs, seed=1000 + k)
+            for _ in range(3):
+                out = engine.ks_pbs_batch(cts, np.full(len(msgs), ids[k], dtype=np.uint32))
+            results[k] = (msgs, out)
+        except Exception as ex:   # surfaced below
+            errors.append(ex)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k, (msgs, out) in results.items():
+        assert list(real_keys.decrypt_batch(out)) == [fs[k](int(m)) for m in msgs], k
+
+
+def test_two_contexts_on_one_device(real_keys):
+    import tfhe_rs_string_b200 as T
+    p = real_keys.params
+    params = T.Params(p.lwe_dimension, p.glwe_dimension, p.polynomial_size, p.pbs_base_log, p.pbs_level,
+                      p.ks_base_log, p.ks_level, p.message_modulus, p.carry_modulus)
+    engines = [T.Engine(params, device=0) for _ in range(2)]
+    try:
+        msgs = np.arange(48) % 16
+        cts = real_keys.encrypt_batch(msgs, seed=77)
+        for e in engines:
+            e.load_ksk(real_keys.ksk)
+            e.load_bsk_standard(real_keys.bsk_standard)
+        outs = [e.ks_pbs_batch(cts, np.full(48, e.generate_lookup_table(lambda x: (x * 7) % 16), dtype=np.uint32)) for e in engines]
+        for o in outs:
+            assert list(real_keys.decrypt_batch(o)) == [(int(m) * 7) % 16 for m in msgs]
+        assert np.array_equal(outs[0], outs[1])   # same kernels, same inputs: deterministic
+    finally:
+        for e in engines:
+            e.close()
