@@ -266,6 +266,28 @@ int launch_pbs_lat(b200tfhe_ctx *ctx, const PbsArgs &a) {
         CU_TRY(ctx, cudaFuncSetAttribute(pbs_lat_kernel<CTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[ctx->device & 15] = true;
     }
+#ifdef B200TFHE_TIMELINE
+    if (const char *dump = getenv("B200TFHE_PBS_TIMELINE")) {
+        PbsArgs b = a;
+        const size_t n = 8 * 8 * 16;
+        CU_TRY(ctx, cudaMalloc(&b.dbg, n * sizeof(long long)));
+        CU_TRY(ctx, cudaMemsetAsync(b.dbg, 0, n * sizeof(long long), ctx->stream));
+        pbs_lat_kernel<CTS><<<(unsigned)((a.batch + CTS - 1) / CTS), CTS == 4 ? 512 : 256, smem, ctx->stream>>>(b);
+        std::vector<long long> h(n);
+        CU_TRY(ctx, cudaMemcpyAsync(h.data(), b.dbg, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(b.dbg);
+        if (FILE *f = fopen(dump, "w")) {
+            for (size_t r = 0; r < 64; r++) {
+                fprintf(f, "%zu %zu", r / 8, r % 8);
+                for (int k = 0; k < 11; k++) fprintf(f, " %lld", h[r * 16 + k]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+        return 0;
+    }
+#endif
     pbs_lat_kernel<CTS><<<(unsigned)((a.batch + CTS - 1) / CTS), CTS == 4 ? 512 : 256, smem, ctx->stream>>>(a);
     return 0;
 }

@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
 
         // ---------------------------------------------------------------- CMUX loop
         for (int i = 0; i < a.n; i++) {
+            PBS3_TS(0);
             double xr[16], xi[16];
             // phase A: ct1 = acc * X^a~ - acc, round + digit, exact int -> double, twist by C_m (see pbs_kernel3.cuh)
             {
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
             }
             // (the barrier inside the first pass also orders both warps' rotation reads before the buffer is reused)
 
+            PBS3_TS(1);
             // ---- forward transform
             double yr[16], yi[16];
             lat_fwd_pass<kTwoRounds>(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);
@@ -315,6 +317,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
                     }
                 }
             }
+            PBS3_TS(2);
             pair_barrier(bar_pair);
 #pragma unroll
             for (int ll = 0; ll < 16; ll++) {
@@ -323,6 +326,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
             }
             lat_fwd_pass<kTwoRounds>(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier also orders the transposition reads before the writes below
 
+            PBS3_TS(3);
             // ---- exchange the transforms between the two polynomials, Out_p = B[p][p] F_p + B[1-p][p] F_{1-p}
 #pragma unroll
             for (int kap = 0; kap < 16; kap++) tb_own[(2 * kap + h) * 32 + lane] = make_double2(yr[kap], yi[kap]);
@@ -337,7 +341,9 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
                     zi[brev4(kap)] = fma(bo.y, yr[kap], bo.x * yi[kap]);
                 }
             }
+            PBS3_TS(4);
             quad_barrier(bar_ct);
+            PBS3_TS(5);
             {
                 const double2 *b_oth = bsk_s + (size_t)((1 - p) * 2 + p) * kHalf + lane;
 #pragma unroll
@@ -354,8 +360,10 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
                 if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
                     issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
             }
+            PBS3_TS(6);
             quad_barrier(bar_ct);   // the sibling polynomial has read this one's transform before the buffer is reused
 
+            PBS3_TS(7);
             // ---- inverse transform
             lat_inv_pass<kTwoRounds>(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // y[ll]: index l = ll + 16 h of lane k1
 #pragma unroll
@@ -379,6 +387,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
             }
             lat_inv_pass<kTwoRounds>(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier orders the transposition reads before the rotation copy below
 
+            PBS3_TS(8);
             // ---- phase D: untwist, from_torus, G -= delta, refresh both copies
             uint64_t dl0[16], dl1[16];
 #pragma unroll
@@ -410,7 +419,9 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
                 }
                 tmem_wait_st();
             }
+            PBS3_TS(9);
             pair_barrier(bar_pair);   // rotation copy complete (both halves) before the next step's gather
+            PBS3_TS(10);
         }
 
         // ---------------------------------------------------------------- sample extraction

@@ -1,7 +1,7 @@
 """Development aid: per-warp phase timeline of CTA 0 of pbs_kernel3 (B200TFHE_PBS_TIMELINE=<file>)."""
 import sys
 import numpy as np
-names = ["A", "fwdFFT", "stsF", "bskwait", "ownmul", "bar1", "othmul", "bar2", "invFFT", "D"]
+names = sys.argv[2].split(",") if len(sys.argv) > 2 else ["A", "fwdFFT", "stsF", "bskwait", "ownmul", "bar1", "othmul", "bar2", "invFFT", "D"]
 rows = [list(map(int, l.split())) for l in open(sys.argv[1])]
 d = {}
 for r in rows:
