@@ -267,6 +267,39 @@ def run_b200(args):
     ms_e2e = timed(step_e2e, e2e_steps, 2)
     e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
 
+    # ---- second half of BASELINE.json's metric: FheString eq (64-char strings, 4 blocks per char; device-
+    # resident inputs, all dependency levels on the GPU): latency of ONE pair on rank 0, and the batch of 256
+    # pairs sharded over the ranks by string (independent units, no collective; max over ranks)
+    str_eq, str_ms, str_err = {}, [0.0, 0.0], 0.0
+    try:   # no collective inside: a failure on one rank must not leave the others waiting
+        from tfhe_rs_string_b200 import multigpu
+        b0, b1 = multigpu.shard_bounds(256, world, rank)
+        for k, (label, n_str) in enumerate((("one_pair_64_chars", 1), ("256_pairs_64_chars", b1 - b0))):
+            prog = T.Program(eng, "string_eq", [max(1, n_str), 64, 64, 4])
+            d_i = torch.from_numpy(rng.integers(-2**63, 2**63, (prog.info["n_inputs"], p.big_lwe_size), dtype=np.int64)).cuda()
+            d_o = torch.empty((prog.info["n_outputs"], p.big_lwe_size), dtype=torch.int64, device="cuda")
+            prog.run_device(d_i, d_o); eng.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                prog.run_device(d_i, d_o)
+            e1.record(stream)
+            eng.sync(); torch.cuda.synchronize()
+            str_ms[k] = e0.elapsed_time(e1) / 3
+            str_eq[label] = {"ms": str_ms[k], "n_pbs_per_rank": prog.info["n_pbs"], "depth": prog.info["depth"],
+                             "strings_per_rank": max(1, n_str)}
+            prog.close()
+    except Exception as ex:   # the headline line must not depend on this extra
+        str_eq, str_err = {"error": str(ex)}, 1.0
+    if dist is not None:
+        t = torch.tensor(str_ms + [str_err], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if float(t[2].item()) == 0.0:
+            str_eq["one_pair_64_chars"]["ms"] = float(t[0].item())
+            str_eq["256_pairs_64_chars"]["ms"] = float(t[1].item())
+        elif "error" not in str_eq:
+            str_eq = {"error": "failed on another rank"}
+
     if rank == 0:
         pbs_ms = kt["pbs_ms"] / max(1, kt["pbs_launches"])
         ks_ms = kt["ks_ms"] / max(1, kt["ks_launches"])
@@ -307,26 +340,7 @@ def run_b200(args):
             "gpu_launches": int(kt["pbs_launches"] + 2 * kt["ks_launches"]),   # per step: ks_digits + ks_mma + pbs
             "clocks": clocks,
         }
-        # second half of BASELINE.json's metric: FheString eq latency (one pair of 64-char strings, 4 blocks
-        # per char; device-resident inputs, all dependency levels on the GPU) and the batch-of-256 time
-        try:
-            lat = {}
-            for label, shape in (("one_pair_64_chars", [1, 64, 64, 4]), ("256_pairs_64_chars", [256, 64, 64, 4])):
-                prog = T.Program(eng, "string_eq", shape)
-                d_i = torch.from_numpy(rng.integers(-2**63, 2**63, (prog.info["n_inputs"], p.big_lwe_size), dtype=np.int64)).cuda()
-                d_o = torch.empty((prog.info["n_outputs"], p.big_lwe_size), dtype=torch.int64, device="cuda")
-                prog.run_device(d_i, d_o); eng.sync()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                for _ in range(3):
-                    prog.run_device(d_i, d_o)
-                e1.record(stream)
-                eng.sync(); torch.cuda.synchronize()
-                lat[label] = {"ms": e0.elapsed_time(e1) / 3, "n_pbs": prog.info["n_pbs"], "depth": prog.info["depth"]}
-                prog.close()
-            line["fhe_string_eq"] = lat
-        except Exception as ex:   # the headline line must not depend on this extra
-            line["fhe_string_eq"] = {"error": str(ex)}
+        line["fhe_string_eq"] = str_eq
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             v, dt, ok, sample = cpu_baseline(args.cpu_sample, threads, B)
