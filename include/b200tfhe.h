@@ -39,8 +39,9 @@ typedef struct b200tfhe_ctx b200tfhe_ctx;
 
 /* shortint/parameters/mod.rs:62-76 (ClassicPBSParameters), KS->PBS order, native modulus.
  * Supported by the kernels today: glwe_dimension = 1, polynomial_size = 2048, pbs_level = 1,
- * ks_base_log <= 7 (PARAM_MESSAGE_2_CARRY_2_KS_PBS, shortint/parameters/mod.rs:703-717, and any
- * parameter set of the same shape with another lwe_dimension / KS decomposition). */
+ * ks_base_log <= 7: all five classic parameter sets of the reference with N = 2048 (PARAM_MESSAGE_1_CARRY_3,
+ * 2_2, 3_1, 4_0 _KS_PBS and 2_2 _PBS_KS, shortint/parameters/mod.rs:688-747,1155-1169), and any set of the
+ * same shape with another lwe_dimension <= 1024 / KS decomposition. */
 typedef struct {
     uint32_t lwe_dimension;   /* n  */
     uint32_t glwe_dimension;  /* k  */
