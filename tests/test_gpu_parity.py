@@ -239,3 +239,14 @@ def test_two_contexts_on_one_device(real_keys):
     finally:
         for e in engines:
             e.close()
+
+
+@pytest.mark.parametrize("batch", [5, 200, 400, 700])
+def test_repeated_runs_are_bit_identical(engine, real_keys, batch):
+    """Same inputs, same kernels: every repetition must give identical bits (a race in the shared-memory /
+    TMEM hand-overs of the PBS kernels would show up here); tools/soak.py is the long version."""
+    cts = real_keys.encrypt_batch(np.arange(batch) % 16, seed=1234 + batch)
+    ids = np.full(batch, engine.generate_lookup_table(lambda x: (x + 3) % 16), dtype=np.uint32)
+    ref = engine.ks_pbs_batch(cts, ids)
+    for _ in range(3):
+        assert np.array_equal(engine.ks_pbs_batch(cts, ids), ref)
