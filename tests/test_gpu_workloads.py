@@ -133,3 +133,40 @@ def test_extra_ops_on_gpu(engine, real_keys):
     assert list(out) == [int(x.startswith(q)) for x, q in zip(s, pats)]
     out, _ = run(engine, real_keys, "string_ends_with", [4, 14, 4, 4], msgs, 676)
     assert list(out) == [int(x.endswith(q)) for x, q in zip(s, pats)]
+
+
+# ---- BASELINE.json shapes at FULL size (the tests above use reduced batches) -----------------------------
+def test_full_size_config2_1024_uint8_pairs(engine, real_keys):
+    rng = np.random.default_rng(31)
+    n = 1024
+    a = rng.integers(0, 256, n); b = rng.integers(0, 256, n); b[::2] = a[::2]
+    msgs = np.concatenate([blocks_of(a).ravel(), blocks_of(b).ravel()])
+    out, info = run(engine, real_keys, "radix_eq", [n, 4], msgs, 700)
+    assert info["n_pbs"] == 5120 and np.array_equal(out, (a == b).astype(U64))
+    out, info = run(engine, real_keys, "radix_add", [n, 4], msgs, 701)
+    assert np.array_equal(from_blocks(out.reshape(n, 4)), ((a + b) % 256).astype(U64))
+
+
+def test_full_size_config3_256_strings_of_64_chars(engine, real_keys):
+    rng = np.random.default_rng(32)
+    n, L = 256, 64
+    a = ["".join(chr(rng.integers(32, 127)) for _ in range(L)) for _ in range(n)]
+    b = list(a)
+    for i in range(0, n, 2):   # half equal, half differing in one random position
+        q = int(rng.integers(0, L)); b[i] = b[i][:q] + chr(32 + (ord(b[i][q]) - 31) % 95) + b[i][q + 1:]
+    out, info = run(engine, real_keys, "string_eq", [n, L, L, 4], np.concatenate([chars(a).ravel(), chars(b).ravel()]), 710)
+    assert info["n_pbs"] == 83456
+    assert list(out) == [int(x == y) for x, y in zip(a, b)]
+
+
+def test_full_size_config5_trivium_1024_bits(engine, real_keys):
+    from oracle import oracle as O
+    k = json.load(open(os.path.join(HERE, "golden", "trivium_kat.json")))["kats"][3]
+    iv = k["iv_bits"]
+    iv_lo = sum(b << i for i, b in enumerate(iv[:64])); iv_hi = sum(b << i for i, b in enumerate(iv[64:]))
+    out, info = run(engine, real_keys, "trivium", [16, iv_lo, iv_hi], np.array(k["key_bits"]), 720)
+    assert len(out) == 1024
+    by = bytes(sum(int(out[8 * i + j]) << j for j in range(8)) for i in range(128))
+    assert by[:64].hex().upper() == k["keystream_bytes_0_63_hex"]          # the reference's known answer
+    clear = O.circuit_run_cleartext("trivium", [16, iv_lo, iv_hi], k["key_bits"])
+    assert np.array_equal(out, clear)                                        # and the cleartext executor beyond it

@@ -19,7 +19,7 @@ CASES = [
     ("string_to_uppercase", [256, 64, 4], "config 3: 256 strings x 64 chars, to_uppercase"),
     ("string_contains", [1, 256, 8, 4], "config 4: contains, 8-char pattern in 256 chars"),
     ("string_find", [1, 256, 8, 4], "config 4: find, 8-char pattern in 256 chars"),
-    ("trivium", [128, 0, 0], "config 5: trivium, 1152 warm-up + 1024 output bits"),
+    ("trivium", [16, 0, 0], "config 5: trivium, 1152 warm-up + 1024 output bits"),
 ]
 sel = sys.argv[1].split(",") if len(sys.argv) > 1 else None
 for op, shape, label in CASES:
