@@ -60,3 +60,26 @@ def test_rust_shim_declares_exactly_the_header_symbols():
     for name, args in rust.items():
         c_args = re.search(r"\bint\s+" + name + r"\s*\((.*?)\)\s*;", hdr, re.S).group(1)
         assert len([a for a in args.split(",") if a.strip()]) == len([a for a in c_args.split(",") if a.strip()]), name
+
+
+def test_header_is_plain_c_and_example_links():
+    """include/b200tfhe.h must be usable from C (no C++ in the boundary) and the example client must link
+    against the built library; without a GPU the example fails loudly at ctx_create."""
+    import subprocess, tempfile
+    import tfhe_rs_string_b200 as T
+    if not os.path.exists(T.lib_path()):
+        import __graft_entry__ as g
+        g.build()
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, "b200tfhe.h")])
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "ks_pbs_example")
+        libdir = os.path.dirname(T.lib_path())
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-I", inc, os.path.join(ROOT, "examples", "ks_pbs_example.c"),
+                               "-L", libdir, "-lb200tfhe", "-Wl,-rpath," + libdir, "-o", exe])
+        import torch
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+        if torch.cuda.is_available():
+            assert r.returncode == 0, r.stderr
+        else:
+            assert r.returncode != 0 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
