@@ -37,11 +37,13 @@ extern "C" {
 
 typedef struct b200tfhe_ctx b200tfhe_ctx;
 
-/* shortint/parameters/mod.rs:62-76 (ClassicPBSParameters), KS->PBS order, native modulus.
- * Supported by the kernels today: glwe_dimension = 1, polynomial_size = 2048, pbs_level = 1,
- * ks_base_log <= 7: all five classic parameter sets of the reference with N = 2048 (PARAM_MESSAGE_1_CARRY_3,
- * 2_2, 3_1, 4_0 _KS_PBS and 2_2 _PBS_KS, shortint/parameters/mod.rs:688-747,1155-1169), and any set of the
- * same shape with another lwe_dimension <= 1024 / KS decomposition. */
+/* shortint/parameters/mod.rs:62-76 (ClassicPBSParameters), native modulus 2^64; either PBS order.
+ * Every classic parameter set of the reference is accepted: glwe_dimension 1..8, polynomial_size 256..32768,
+ * any PBS / KS decomposition with base_log*level < 64, lwe_dimension <= 4096.  Sets with glwe_dimension = 1,
+ * polynomial_size = 2048, pbs_level = 1, pbs_base_log = 23 (PARAM_MESSAGE_1_CARRY_3, 2_2, 3_1, 4_0 _KS_PBS and
+ * 2_2 _PBS_KS, shortint/parameters/mod.rs:688-747,1155-1169) run on the specialised kernels (pbs_kernel3 /
+ * pbs_lat_kernel); all others (1_1 k=3 N=512 :613-627, 3_3 N=8192 l=2 :853-867, 4_4 N=32768 :1063-1077, ...) on the
+ * generic one-CTA-per-ciphertext kernel (csrc/pbs_generic.cuh). */
 typedef struct {
     uint32_t lwe_dimension;   /* n  */
     uint32_t glwe_dimension;  /* k  */
@@ -56,6 +58,14 @@ typedef struct {
  * in multi-GPU runs).  Replaces ShortintEngine's thread-local scratch (shortint/engine/mod.rs:
  * 23-25,40-69): all scratch lives on the device and is owned by the context. */
 int b200tfhe_ctx_create(const b200tfhe_params *params, int device, b200tfhe_ctx **out);
+/* One context over several GPUs of one box (the reference's analogue is the rayon fan-out of
+ * benches/core_crypto/pbs_bench.rs:517-531).  Keys are uploaded and converted once on devices[0] and copied GPU to
+ * GPU (cudaMemcpyPeerAsync, NVLink); LUTs are registered on every GPU; every host-buffer batch call is cut into
+ * contiguous shards, one per GPU, each pipelined by its own host thread and streams; named programs are split over
+ * their independent units (integers, strings).  There is no per-PBS collective.  "_device" entry points act on
+ * devices[0]; b200tfhe_ks_pbs_batch_device_multi takes one device-resident shard per GPU. */
+int b200tfhe_ctx_create_multi(const b200tfhe_params *params, const int *devices, int n_devices, b200tfhe_ctx **out);
+int b200tfhe_ctx_device_count(const b200tfhe_ctx *ctx, int *n_devices);
 int b200tfhe_ctx_destroy(b200tfhe_ctx *ctx);
 int b200tfhe_last_error(const b200tfhe_ctx *ctx, char *buf, size_t buf_len);
 /* Last error of a failed b200tfhe_ctx_create (no context exists yet). */
@@ -69,11 +79,30 @@ int b200tfhe_load_ksk(b200tfhe_ctx *ctx, const uint64_t *ksk, size_t n_u64);
  * GPU to this library's Fourier layout (replaces par_convert_standard_lwe_bootstrap_key_to_fourier,
  * algorithms/lwe_bootstrap_key_conversion.rs:99+). */
 int b200tfhe_load_bsk_standard(b200tfhe_ctx *ctx, const uint64_t *bsk, size_t n_u64);
-/* Device-resident key arena (Fourier BSK || KSK || KS column sums), contiguous, so a multi-GPU
- * launcher can broadcast it once (NCCL) instead of re-uploading: rank 0 loads keys, every rank
- * passes its arena pointer to the collective, then non-root ranks call b200tfhe_keys_adopt(). */
+/* Device-resident key arena of devices[0] (Fourier BSK || KSK || KSK byte limbs), contiguous, so a one-process-per-GPU
+ * launcher can broadcast it once (NCCL) instead of re-uploading: rank 0 loads keys, every rank passes its arena
+ * pointer to the collective, then non-root ranks call b200tfhe_keys_adopt() (which also replicates the arena to the
+ * other GPUs of a multi-GPU context). */
 int b200tfhe_key_arena(b200tfhe_ctx *ctx, void **device_ptr, size_t *bytes);
 int b200tfhe_keys_adopt(b200tfhe_ctx *ctx);
+
+/* ---- server key wire format (csrc/key_import.hpp; PARITY UNPINNED: no Rust toolchain in the build image) ------ */
+/* Where the key material sits inside a serialised server key.  Offsets are in bytes from the start of the buffer;
+ * serde does not align, so copy before reinterpreting. */
+typedef struct {
+    uint64_t ksk_offset, ksk_len;          /* ksk_len u64 words, reference KSK layout                            */
+    uint64_t bsk_offset, bsk_len;          /* standard key: bsk_len u64 words; Fourier key: bsk_len complex f64  */
+    uint64_t bsk_poly_stride_bytes;        /* distance between consecutive polynomials (Fourier: 8-byte length prefix each) */
+    uint32_t bsk_is_fourier;               /* 1: bincode(shortint::ServerKey), Fourier key in concrete-fft's serialisation order */
+    uint32_t pbs_order;                    /* 0 = KeyswitchBootstrap, 1 = BootstrapKeyswitch (commons/parameters.rs:234-245) */
+    uint64_t max_degree, max_noise_level;  /* ServerKey metadata (0 for the standard-domain bundle)               */
+} b200tfhe_key_view;
+/* Parses bincode(shortint::ServerKey) (shortint/server_key/mod.rs:283-297) or the standard-domain bundle
+ * (LweKeyswitchKey<Vec<u64>>, LweBootstrapKey<Vec<u64>>, MessageModulus, CarryModulus, PBSOrder) written by the Rust
+ * shim; fills the parameter set and the view.  Needs no GPU. */
+int b200tfhe_parse_server_key(const uint8_t *bytes, size_t n_bytes, b200tfhe_params *params, b200tfhe_key_view *view);
+/* Parses and uploads both keys.  The context must have been created with the key's dimensions and decompositions. */
+int b200tfhe_load_server_key_bytes(b200tfhe_ctx *ctx, const uint8_t *bytes, size_t n_bytes);
 
 /* ---- lookup tables -------------------------------------------------------------------- */
 /* Registers a GLWE accumulator ((k+1)*N u64, as produced by generate_lookup_table /
@@ -109,6 +138,12 @@ int b200tfhe_keyswitch_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, uin
 int b200tfhe_pbs_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const uint32_t *d_lut_id, uint64_t *d_out, size_t batch);
 int b200tfhe_ks_pbs_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const uint32_t *d_lut_id, uint64_t *d_out, size_t batch);
 int b200tfhe_pbs_ks_batch_device(b200tfhe_ctx *ctx, const uint64_t *d_in, const uint32_t *d_lut_id, uint64_t *d_out, size_t batch);
+/* Multi-GPU contexts: element i of every array belongs to GPU i of the context (pointers resident on that GPU,
+ * batch[i] ciphertexts; d_lut_id or d_lut_id[i] may be NULL).  Asynchronous on every GPU; b200tfhe_sync waits for all. */
+int b200tfhe_ks_pbs_batch_device_multi(b200tfhe_ctx *ctx, const uint64_t *const *d_in, const uint32_t *const *d_lut_id,
+                                       uint64_t *const *d_out, const size_t *batch);
+/* Lookup-table ids of device-buffer calls cannot be checked on the host: the kernels check them, use table 0 for an
+ * out-of-range id and raise a flag that the next b200tfhe_sync reports as an error. */
 /* lwe_linear_algebra.rs (:68 add, :276 plaintext add, :556 cleartext mul, :703 sub) and the
  * bivariate pack (shortint/server_key/bivariate_pbs.rs:173-181), one launch:
  *   out[b] = ca[b] * x[ia[b]] + cb[b] * y[ib[b]];  out[b].body += pt[b]
@@ -128,11 +163,8 @@ int b200tfhe_set_profiling(b200tfhe_ctx *ctx, int enabled);
 /* Accumulated device time (ms) and launch counts since the last reset; synchronises. */
 int b200tfhe_get_kernel_times(b200tfhe_ctx *ctx, double *ks_ms, uint64_t *ks_launches, double *pbs_ms,
                               uint64_t *pbs_launches, int reset);
-/* Selects the PBS kernel variant (all keep the accumulator in TMEM; 4 ciphertexts per CTA unless
- * stated): 3 = default (pbs_kernel3.cuh: biased accumulator, transform exchange); 0 = previous
- * generation, BSK slice staged once per CTA in shared memory by a bulk async copy; 1 = BSK read
- * from L2 by every warp; 2 = 6 ciphertexts per CTA, BSK read from L2. */
-int b200tfhe_set_pbs_variant(b200tfhe_ctx *ctx, int variant);
+/* Kernels launched by this library on all GPUs of the context since it was created. */
+int b200tfhe_kernel_launch_count(b200tfhe_ctx *ctx, uint64_t *count);
 
 /* ---- batched call sites: level-synchronous programs ---------------------------------- */
 /* The reference's integer / FheString / Trivium layers issue vectors of independent (ciphertext,
@@ -147,6 +179,25 @@ int b200tfhe_set_pbs_variant(b200tfhe_ctx *ctx, int variant);
 typedef struct b200tfhe_program b200tfhe_program;
 int b200tfhe_program_create(b200tfhe_ctx *ctx, const char *op, const uint64_t *shape, size_t n_shape,
                             b200tfhe_program **out);
+/* A caller-built schedule: what the reference's integer layer would hand over instead of one apply_lookup_table call
+ * per block.  Blocks 0..n_inputs-1 are the inputs; node j produces block n_inputs + j =
+ *     LUT[node_lut[j]]( sum_{t in [node_term_begin[j], node_term_begin[j+1])} term_coeff[t] * block[term_block[t]]
+ *                        + node_plaintext[j] * delta )
+ * or just the linear combination when node_lut[j] < 0.  Nodes may only reference earlier blocks; the library levels
+ * the DAG and runs one lwe-linear launch + one KS+PBS launch per dependency level, everything resident in HBM.
+ * luts: n_luts tables of message_modulus*carry_modulus function values (as for b200tfhe_register_lut_from_table).
+ * Degree / noise bookkeeping stays with the caller, as for apply_lookup_table itself. */
+typedef struct {
+    size_t n_inputs, n_nodes, n_luts, n_outputs;
+    const uint32_t *node_term_begin;   /* n_nodes + 1 */
+    const int32_t *term_block;         /* block ids */
+    const int64_t *term_coeff;         /* small signed scalars */
+    const uint64_t *node_plaintext;    /* n_nodes message-space constants, or NULL */
+    const int32_t *node_lut;           /* n_nodes indices into luts, -1 = linear only */
+    const uint64_t *luts;              /* n_luts * message_modulus * carry_modulus */
+    const int32_t *outputs;            /* n_outputs block ids */
+} b200tfhe_circuit_desc;
+int b200tfhe_program_create_from_circuit(b200tfhe_ctx *ctx, const b200tfhe_circuit_desc *desc, b200tfhe_program **out);
 /* info[0..5] = n_inputs, n_outputs, n_pbs, depth, n_stages, n_luts */
 int b200tfhe_program_info(const b200tfhe_program *prog, uint64_t *info);
 int b200tfhe_program_run(b200tfhe_program *prog, const uint64_t *in, uint64_t *out);              /* host buffers, synchronous */
@@ -158,6 +209,12 @@ int b200tfhe_program_destroy(b200tfhe_program *prog);
  * Mirrors the reference's FFT product test, fft_impl/fft64/math/fft/tests.rs:82-222. */
 int b200tfhe_debug_negacyclic_mul(b200tfhe_ctx *ctx, const uint64_t *a_int, const uint64_t *b_torus,
                                   uint64_t *out, size_t count);
+/* The production bootstrap kernel selected for `batch`, stopped after the first `steps` CMUX steps (in_small: batch x
+ * (steps + 1) words = mask prefix and body).  With steps = 1 this is ONE external product on caller data: both
+ * implementations see identical digits, so the GPU and the CPU oracle must agree to FFT rounding (tests assert
+ * 2^42); mirrors fft_impl/common.rs:145-304, which tests the bootstrap against its definition. */
+int b200tfhe_debug_pbs_steps(b200tfhe_ctx *ctx, const uint64_t *in_small, const uint32_t *lut_id, uint64_t *out,
+                             size_t batch, uint32_t steps);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,7 @@ def lib():
         "orc_blind_rotate": (None, [KS, _u64p, _u64p]),
         "orc_bootstrap": (None, [KS, _u64p, _u64p, _u64p]),
         "orc_ks_pbs": (None, [KS, _u64p, _u64p, _u64p]),
+        "orc_bootstrap_steps": (None, [KS, _u64p, C.c_uint32, _u64p, _u64p]),
         "orc_ks_pbs_batch": (None, [KS, _u64p, _u64p, _u32p, _u64p, C.c_size_t, C.c_int]),
         "orc_fill_accumulator": (C.c_uint64, [PP, _u64p, _u64p]),
         "orc_trivial_pbs": (C.c_uint64, [PP, C.c_uint64, _u64p]),
@@ -133,6 +134,26 @@ def params_message_2_carry_2_pbs_ks():
     p.lwe_modular_std_dev = 0.0000006791658447437413
     p.glwe_modular_std_dev = 0.00000000000000029403601535432533
     p.ks_base_log, p.ks_level = 4, 4
+    return p
+
+
+def params_message_1_carry_1():
+    """PARAM_MESSAGE_1_CARRY_1_KS_PBS (shortint/parameters/mod.rs:613-627): k = 3, N = 512."""
+    p = params_message_2_carry_2()
+    p.lwe_dimension, p.glwe_dimension, p.polynomial_size = 684, 3, 512
+    p.lwe_modular_std_dev, p.glwe_modular_std_dev = 0.00002043784477291318, 0.0000000000034525330484572114
+    p.pbs_base_log, p.pbs_level, p.ks_base_log, p.ks_level = 18, 1, 4, 3
+    p.message_modulus, p.carry_modulus = 2, 2
+    return p
+
+
+def params_message_3_carry_3():
+    """PARAM_MESSAGE_3_CARRY_3_KS_PBS (shortint/parameters/mod.rs:853-867): N = 8192, two PBS levels."""
+    p = params_message_2_carry_2()
+    p.lwe_dimension, p.glwe_dimension, p.polynomial_size = 864, 1, 8192
+    p.lwe_modular_std_dev, p.glwe_modular_std_dev = 0.000000757998020150446, 0.0000000000000000002168404344971009
+    p.pbs_base_log, p.pbs_level, p.ks_base_log, p.ks_level = 15, 2, 3, 6
+    p.message_modulus, p.carry_modulus = 8, 8
     return p
 
 
@@ -213,6 +234,15 @@ class Keyset:
         for i in range(small_cts.shape[0]):
             li = 0 if lut_idx is None else int(lut_idx[i])
             self.L.orc_bootstrap(self.h, small_cts[i], luts[li], out[i])
+        return out
+
+    def bootstrap_steps_batch(self, small_prefix, steps, lut):
+        """The bootstrap stopped after `steps` CMUX steps (small_prefix: batch x (steps + 1): mask prefix, body)."""
+        cts = np.ascontiguousarray(small_prefix, dtype=np.uint64).reshape(-1, steps + 1)
+        lut = np.ascontiguousarray(lut, dtype=np.uint64)
+        out = np.zeros((cts.shape[0], self.params.big_lwe_size), dtype=np.uint64)
+        for i in range(cts.shape[0]):
+            self.L.orc_bootstrap_steps(self.h, cts[i], steps, lut, out[i])
         return out
 
     def ks_pbs_batch(self, cts, luts, lut_idx=None, n_threads=None):

@@ -90,6 +90,9 @@ struct FftPlan {
     std::vector<double> tw_re, tw_im; /* twisties: exp(i*pi*j/N), j < n  (fft/mod.rs:58-69) */
     std::vector<double> st_re, st_im; /* per-stage twiddles exp(-2*pi*i*t/len), packed */
     std::vector<uint32_t> brev;
+    /* n == 1024 only: 32 x 32 four-step transform, vectorised across the 32 columns (see fft_forward_1024) */
+    std::vector<double> w32_re, w32_im;   /* [stage 0..4][t < 16]: exp(-2 pi i t / (2 half)), half = 16 >> stage */
+    std::vector<double> t4_re, t4_im;     /* [r < 32][j2 < 32]: exp(-2 pi i j2 brev5(r) / 1024) */
 };
 
 const FftPlan &get_plan(uint32_t N) {
@@ -123,6 +126,26 @@ const FftPlan &get_plan(uint32_t N) {
         for (uint32_t b = 0; b < lg; b++) r |= ((i >> b) & 1u) << (lg - 1 - b);
         p->brev[i] = r;
     }
+    if (n == 1024) {
+        const long double pi = 3.14159265358979323846264338327950288L;
+        p->w32_re.assign(5 * 16, 1.0); p->w32_im.assign(5 * 16, 0.0);
+        for (int st = 0; st < 5; st++) {
+            const int half = 16 >> st;
+            for (int t = 0; t < half; t++) {
+                long double a = -2.0L * pi * (long double)t / (long double)(2 * half);
+                p->w32_re[st * 16 + t] = (double)cosl(a); p->w32_im[st * 16 + t] = (double)sinl(a);
+            }
+        }
+        p->t4_re.resize(1024); p->t4_im.resize(1024);
+        for (int r = 0; r < 32; r++) {
+            int k1 = 0;
+            for (int b = 0; b < 5; b++) k1 |= ((r >> b) & 1) << (4 - b);
+            for (int j2 = 0; j2 < 32; j2++) {
+                long double a = -2.0L * pi * (long double)(j2 * k1) / 1024.0L;
+                p->t4_re[r * 32 + j2] = (double)cosl(a); p->t4_im[r * 32 + j2] = (double)sinl(a);
+            }
+        }
+    }
     auto &ref = *p;
     plans[N] = std::move(p);
     return ref;
@@ -134,8 +157,87 @@ const FftPlan &get_plan(uint32_t N) {
  * Fourier-domain operation on this path is pointwise. */
 static inline size_t stage_off(uint32_t len) { return (size_t)len / 2 - 1; }
 
+/* ---- n = 1024 (N = 2048, the headline parameter set): 32 x 32 four-step transform.  The reference gets its speed
+ * from concrete-fft's SIMD kernels (fft/mod.rs:161: a plan measured at run time); this is the CPU baseline's
+ * equivalent: every loop runs over the 32 contiguous columns of a row, so the compiler vectorises it (AVX2 /
+ * AVX-512 clones selected at load time, see ORC_SIMD).  View the input as A[j1][j2] (j = 32 j1 + j2):
+ *   pass 1  32-point DIF over j1 for all columns j2      -> row r holds k1 = brev5(r)
+ *   twiddle times exp(-2 pi i j2 k1 / 1024), transpose   -> C[j2][r]
+ *   pass 2  32-point DIF over j2 for all columns r       -> row s holds k2 = brev5(s): D[s][r] = X[k1 + 32 k2]
+ * The inverse runs the same steps backwards (DIT, conjugated).  The Fourier-domain order is a fixed permutation,
+ * which is free: every Fourier-domain operation on this path is pointwise. */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define ORC_SIMD __attribute__((target_clones("arch=x86-64-v4", "arch=x86-64-v3", "default")))
+#else
+#define ORC_SIMD
+#endif
+
+ORC_SIMD static void cols32_dif(double *__restrict re, double *__restrict im, const double *__restrict wr, const double *__restrict wi) {
+    for (int st = 0, half = 16; half >= 1; st++, half >>= 1)
+        for (int base = 0; base < 32; base += 2 * half)
+            for (int t = 0; t < half; t++) {
+                double *__restrict ar = re + (base + t) * 32, *__restrict ai = im + (base + t) * 32;
+                double *__restrict br = ar + half * 32, *__restrict bi = ai + half * 32;
+                const double cr = wr[st * 16 + t], ci = wi[st * 16 + t];
+                for (int c = 0; c < 32; c++) {
+                    const double dr = ar[c] - br[c], di = ai[c] - bi[c];
+                    ar[c] += br[c]; ai[c] += bi[c];
+                    br[c] = dr * cr - di * ci;
+                    bi[c] = dr * ci + di * cr;
+                }
+            }
+}
+ORC_SIMD static void cols32_dit_conj(double *__restrict re, double *__restrict im, const double *__restrict wr, const double *__restrict wi) {
+    for (int st = 4, half = 1; half <= 16; st--, half <<= 1)
+        for (int base = 0; base < 32; base += 2 * half)
+            for (int t = 0; t < half; t++) {
+                double *__restrict ar = re + (base + t) * 32, *__restrict ai = im + (base + t) * 32;
+                double *__restrict br = ar + half * 32, *__restrict bi = ai + half * 32;
+                const double cr = wr[st * 16 + t], ci = wi[st * 16 + t];
+                for (int c = 0; c < 32; c++) {
+                    const double xr = br[c] * cr + bi[c] * ci, xi = bi[c] * cr - br[c] * ci;   /* b * conj(w) */
+                    br[c] = ar[c] - xr; bi[c] = ai[c] - xi;
+                    ar[c] += xr; ai[c] += xi;
+                }
+            }
+}
+/* out[j2][r] = in[r][j2] * (tr + i ti)[r][j2]   (CONJ: conj twiddle applied after the transpose: out[r][j2] = in[j2][r] * conj t[r][j2]) */
+ORC_SIMD static void twiddle_transpose(const double *__restrict ir, const double *__restrict ii, double *__restrict orr, double *__restrict oi,
+                                       const double *__restrict tr, const double *__restrict ti) {
+    for (int r = 0; r < 32; r++)
+        for (int c = 0; c < 32; c++) {
+            const double a = ir[r * 32 + c], b = ii[r * 32 + c], x = tr[r * 32 + c], y = ti[r * 32 + c];
+            orr[c * 32 + r] = a * x - b * y;
+            oi[c * 32 + r] = a * y + b * x;
+        }
+}
+ORC_SIMD static void transpose_twiddle_conj(const double *__restrict ir, const double *__restrict ii, double *__restrict orr, double *__restrict oi,
+                                            const double *__restrict tr, const double *__restrict ti) {
+    for (int r = 0; r < 32; r++)
+        for (int c = 0; c < 32; c++) {
+            const double a = ir[c * 32 + r], b = ii[c * 32 + r], x = tr[r * 32 + c], y = -ti[r * 32 + c];
+            orr[r * 32 + c] = a * x - b * y;
+            oi[r * 32 + c] = a * y + b * x;
+        }
+}
+static void fft_forward_1024(const FftPlan &pl, double *re, double *im) {
+    alignas(64) double tr[1024], ti[1024];
+    cols32_dif(re, im, pl.w32_re.data(), pl.w32_im.data());
+    twiddle_transpose(re, im, tr, ti, pl.t4_re.data(), pl.t4_im.data());
+    cols32_dif(tr, ti, pl.w32_re.data(), pl.w32_im.data());
+    std::memcpy(re, tr, sizeof(tr)); std::memcpy(im, ti, sizeof(ti));
+}
+static void fft_inverse_1024(const FftPlan &pl, double *re, double *im) {
+    alignas(64) double tr[1024], ti[1024];
+    cols32_dit_conj(re, im, pl.w32_re.data(), pl.w32_im.data());
+    transpose_twiddle_conj(re, im, tr, ti, pl.t4_re.data(), pl.t4_im.data());
+    cols32_dit_conj(tr, ti, pl.w32_re.data(), pl.w32_im.data());
+    std::memcpy(re, tr, sizeof(tr)); std::memcpy(im, ti, sizeof(ti));
+}
+
 void fft_forward(const FftPlan &pl, double *__restrict re, double *__restrict im) {
     const uint32_t n = pl.n;
+    if (n == 1024) return fft_forward_1024(pl, re, im);
     for (uint32_t len = n; len >= 2; len >>= 1) {
         const uint32_t half = len / 2;
         const double *__restrict wr = &pl.st_re[stage_off(len)], *__restrict wi = &pl.st_im[stage_off(len)];
@@ -154,6 +256,7 @@ void fft_forward(const FftPlan &pl, double *__restrict re, double *__restrict im
 
 void fft_inverse(const FftPlan &pl, double *__restrict re, double *__restrict im) {
     const uint32_t n = pl.n;
+    if (n == 1024) return fft_inverse_1024(pl, re, im);
     for (uint32_t len = 2; len <= n; len <<= 1) {
         const uint32_t half = len / 2;
         const double *__restrict wr = &pl.st_re[stage_off(len)], *__restrict wi = &pl.st_im[stage_off(len)];
@@ -535,9 +638,11 @@ static void add_external_product(const orc_params &p, const FftPlan &pl, uint64_
 }
 
 /* fft_impl/fft64/crypto/bootstrap.rs:242-331 */
-static void blind_rotate(const orc_keyset *ks, const uint64_t *lwe, uint64_t *acc, Scratch &s) {
+/* n_steps < n stops the CMUX loop early (test hook: one external product on identical inputs pins the Fourier stage
+ * without the decomposer random walk); the body is then read at lwe[n_steps]. */
+static void blind_rotate(const orc_keyset *ks, const uint64_t *lwe, uint64_t *acc, Scratch &s, uint32_t n_steps = UINT32_MAX) {
     const orc_params &p = ks->p;
-    const uint32_t n = p.lwe_dimension, k = p.glwe_dimension, N = p.polynomial_size;
+    const uint32_t n = std::min(p.lwe_dimension, n_steps), k = p.glwe_dimension, N = p.polynomial_size;
     uint32_t log2N = 0;
     while ((1u << log2N) < N) log2N++;
     const FftPlan &pl = get_plan(N);
@@ -574,6 +679,14 @@ static void bootstrap(const orc_keyset *ks, const uint64_t *lwe_small, const uin
 void orc_bootstrap(const orc_keyset *ks, const uint64_t *lwe_small, const uint64_t *lut, uint64_t *out_big) {
     Scratch s(ks->p.glwe_dimension, ks->p.polynomial_size);
     bootstrap(ks, lwe_small, lut, out_big, s);
+}
+
+void orc_bootstrap_steps(const orc_keyset *ks, const uint64_t *lwe_prefix, uint32_t n_steps, const uint64_t *lut, uint64_t *out_big) {
+    const uint32_t k = ks->p.glwe_dimension, N = ks->p.polynomial_size;
+    Scratch s(k, N);
+    std::vector<uint64_t> acc(lut, lut + (size_t)(k + 1) * N);
+    blind_rotate(ks, lwe_prefix, acc.data(), s, n_steps);
+    sample_extract0(out_big, acc.data(), k, N);
 }
 
 /* shortint/server_key/mod.rs:783-857 (classic branch, non trivial input) */

@@ -87,6 +87,9 @@ void orc_keyswitch_raw(const uint64_t *ksk, uint32_t in_dim, uint32_t out_dim, u
 void orc_blind_rotate(const orc_keyset *ks, const uint64_t *lwe_small, uint64_t *acc_glwe);
 void orc_bootstrap(const orc_keyset *ks, const uint64_t *lwe_small, const uint64_t *lut_glwe,
                    uint64_t *out_big);
+/* test hook: the bootstrap stopped after the first n_steps CMUX steps; lwe_prefix = n_steps mask words then the body */
+void orc_bootstrap_steps(const orc_keyset *ks, const uint64_t *lwe_prefix, uint32_t n_steps, const uint64_t *lut_glwe,
+                         uint64_t *out_big);
 void orc_ks_pbs(const orc_keyset *ks, const uint64_t *in_big, const uint64_t *lut_glwe,
                 uint64_t *out_big);
 /* luts: n_luts GLWE accumulators ((k+1)*N u64 each); lut_idx[b] selects per ciphertext */

@@ -34,9 +34,42 @@ pub struct b200tfhe_params {
     pub carry_modulus: u32,
 }
 
+/// Where the key material sits inside a serialised server key (b200tfhe_parse_server_key).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct b200tfhe_key_view {
+    pub ksk_offset: u64,
+    pub ksk_len: u64,
+    pub bsk_offset: u64,
+    pub bsk_len: u64,
+    pub bsk_poly_stride_bytes: u64,
+    pub bsk_is_fourier: u32,
+    pub pbs_order: u32,
+    pub max_degree: u64,
+    pub max_noise_level: u64,
+}
+
+/// A caller-built level schedule (b200tfhe_program_create_from_circuit).
+#[repr(C)]
+pub struct b200tfhe_circuit_desc {
+    pub n_inputs: usize,
+    pub n_nodes: usize,
+    pub n_luts: usize,
+    pub n_outputs: usize,
+    pub node_term_begin: *const u32,
+    pub term_block: *const i32,
+    pub term_coeff: *const i64,
+    pub node_plaintext: *const u64,
+    pub node_lut: *const i32,
+    pub luts: *const u64,
+    pub outputs: *const i32,
+}
+
 #[link(name = "b200tfhe")]
 extern "C" {
     pub fn b200tfhe_ctx_create(params: *const b200tfhe_params, device: c_int, out: *mut *mut b200tfhe_ctx) -> c_int;
+    pub fn b200tfhe_ctx_create_multi(params: *const b200tfhe_params, devices: *const c_int, n_devices: c_int, out: *mut *mut b200tfhe_ctx) -> c_int;
+    pub fn b200tfhe_ctx_device_count(ctx: *const b200tfhe_ctx, n_devices: *mut c_int) -> c_int;
     pub fn b200tfhe_ctx_destroy(ctx: *mut b200tfhe_ctx) -> c_int;
     pub fn b200tfhe_last_error(ctx: *const b200tfhe_ctx, buf: *mut c_char, buf_len: usize) -> c_int;
     pub fn b200tfhe_last_global_error(buf: *mut c_char, buf_len: usize) -> c_int;
@@ -64,7 +97,18 @@ extern "C" {
     pub fn b200tfhe_get_kernel_times(
         ctx: *mut b200tfhe_ctx, ks_ms: *mut f64, ks_launches: *mut u64, pbs_ms: *mut f64, pbs_launches: *mut u64, reset: c_int,
     ) -> c_int;
-    pub fn b200tfhe_set_pbs_variant(ctx: *mut b200tfhe_ctx, variant: c_int) -> c_int;
+    pub fn b200tfhe_kernel_launch_count(ctx: *mut b200tfhe_ctx, count: *mut u64) -> c_int;
+    pub fn b200tfhe_ks_pbs_batch_device_multi(
+        ctx: *mut b200tfhe_ctx, d_in: *const *const u64, d_lut_id: *const *const u32, d_out: *const *mut u64, batch: *const usize,
+    ) -> c_int;
+    pub fn b200tfhe_parse_server_key(bytes: *const u8, n_bytes: usize, params: *mut b200tfhe_params, view: *mut b200tfhe_key_view) -> c_int;
+    pub fn b200tfhe_load_server_key_bytes(ctx: *mut b200tfhe_ctx, bytes: *const u8, n_bytes: usize) -> c_int;
+    pub fn b200tfhe_program_create_from_circuit(
+        ctx: *mut b200tfhe_ctx, desc: *const b200tfhe_circuit_desc, out: *mut *mut b200tfhe_program,
+    ) -> c_int;
+    pub fn b200tfhe_debug_pbs_steps(
+        ctx: *mut b200tfhe_ctx, in_small: *const u64, lut_id: *const u32, out: *mut u64, batch: usize, steps: u32,
+    ) -> c_int;
     pub fn b200tfhe_program_create(
         ctx: *mut b200tfhe_ctx, op: *const c_char, shape: *const u64, n_shape: usize, out: *mut *mut b200tfhe_program,
     ) -> c_int;
@@ -96,9 +140,11 @@ impl B200Engine {
 
     /// `ksk` = `key_switching_key.as_ref()`, `bsk_standard` = `bootstrap_key.as_ref()` taken where
     /// the reference still holds the standard-domain key (shortint/engine/server_side.rs:63-86).
-    pub fn new(params: b200tfhe_params, device: i32, ksk: &[u64], bsk_standard: &[u64]) -> Result<Self, B200Error> {
+    /// `devices`: the GPUs of this box the engine may use (one context over all of them: every batch
+    /// call is cut into one contiguous shard per GPU inside the library).
+    pub fn new(params: b200tfhe_params, devices: &[i32], ksk: &[u64], bsk_standard: &[u64]) -> Result<Self, B200Error> {
         let mut ctx = ptr::null_mut();
-        if unsafe { b200tfhe_ctx_create(&params, device, &mut ctx) } != 0 {
+        if unsafe { b200tfhe_ctx_create_multi(&params, devices.as_ptr(), devices.len() as c_int, &mut ctx) } != 0 {
             return Err(Self::err(ptr::null()));
         }
         let e = B200Engine { ctx, big_size: (params.glwe_dimension * params.polynomial_size + 1) as usize };
@@ -119,7 +165,9 @@ impl B200Engine {
         }
     }
 
-    /// Batched `keyswitch_programmable_bootstrap_assign` on flat LWE buffers (in place).
+    /// Batched `keyswitch_programmable_bootstrap_assign` on flat LWE buffers (in place).  `cts` may be an
+    /// ordinary (pageable) `Vec<u64>`: the library stages it wave by wave through its own pinned slabs, so
+    /// the copies still run under the kernels (measured within a few % of a pinned buffer).
     pub fn ks_pbs_batch(&self, cts: &mut [u64], lut_ids: &[u32]) -> Result<(), B200Error> {
         let batch = lut_ids.len();
         assert_eq!(cts.len(), batch * self.big_size);

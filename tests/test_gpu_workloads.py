@@ -159,6 +159,17 @@ def test_full_size_config3_256_strings_of_64_chars(engine, real_keys):
     assert list(out) == [int(x == y) for x, y in zip(a, b)]
 
 
+def test_full_size_config3_to_uppercase_256_strings(engine, real_keys):
+    """BASELINE configs[2], second half: to_uppercase on 256 strings of 64 chars (294,912 PBS, depth 7)."""
+    rng = np.random.default_rng(33)
+    n, L = 256, 64
+    a = ["".join(chr(rng.integers(32, 127)) for _ in range(L)) for _ in range(n)]
+    out, info = run(engine, real_keys, "string_to_uppercase", [n, L, 4], chars(a).ravel(), 711)
+    assert info["n_pbs"] == 294912
+    got = from_blocks(out.reshape(n, L, 4))
+    assert ["".join(chr(int(c)) for c in row) for row in got] == [s.upper() for s in a]
+
+
 def test_full_size_config5_trivium_1024_bits(engine, real_keys):
     from oracle import oracle as O
     k = json.load(open(os.path.join(HERE, "golden", "trivium_kat.json")))["kats"][3]

@@ -23,6 +23,7 @@
 #include <functional>
 #include <map>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace b200 {
@@ -118,7 +119,22 @@ class Circuit {
     }
 
     // ---- bootstrap: one node, or host evaluation when the input is a constant
+    // The reference guards every lookup with its Degree / MaxDegree bookkeeping (checked and smart operations,
+    // shortint/server_key/mod.rs:1040-1100): a value that can reach the padding bit would be bootstrapped through the
+    // negacyclic half of the table.  Same rule here: the tracked upper bound must stay below
+    // message_modulus * carry_modulus (pbs_unchecked is the explicit opt-out, e.g. for caller-built schedules).
     Lin pbs(const Lin &x, int lut_id, uint32_t out_degree) {
+        if (!x.is_const() && x.degree >= modulus_sup())
+            throw std::logic_error("pbs: operand degree " + std::to_string(x.degree) + " can reach the padding bit (>= " +
+                                   std::to_string(modulus_sup()) + "); propagate carries first");
+        return pbs_unchecked(x, lut_id, out_degree);
+    }
+    Lin pbs_unchecked(const Lin &x, int lut_id) {
+        uint64_t mx = 0;
+        for (uint64_t v : luts.at(lut_id)) mx = std::max(mx, v);
+        return pbs_unchecked(x, lut_id, (uint32_t)mx);
+    }
+    Lin pbs_unchecked(const Lin &x, int lut_id, uint32_t out_degree) {
         if (lut_id < 0 || lut_id >= (int)luts.size()) throw std::out_of_range("lut id");
         if (x.is_const()) {
             // trivial_pbs_assign: value = body / delta; negate the table entry when the padding bit is set
@@ -150,6 +166,14 @@ class Circuit {
         r.terms.push_back({new_node(x, -1), 1});
         // the node itself runs right after the level that produced its operands (stage key 2L+1);
         // anything that consumes the materialised block is scheduled from the next level on
+        r.level = x.level + 1;
+        r.degree = x.degree;
+        return r;
+    }
+    // like materialize, but always a fresh block (a caller-built schedule addresses nodes by position)
+    Lin materialize_always(const Lin &x) {
+        Lin r;
+        r.terms.push_back({new_node(x, -1), 1});
         r.level = x.level + 1;
         r.degree = x.degree;
         return r;

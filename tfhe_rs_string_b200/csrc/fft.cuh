@@ -27,8 +27,17 @@ constexpr int kHalf = 1024;      // complex points
 constexpr int kTStride = 33;     // padded row stride (in double2) of the transposition buffer
 constexpr int kTBufElems = 32 * kTStride;  // double2 elements per warp buffer (16,896 B)
 
-__device__ __constant__ double2 c_w32[16] = {B200_W32_TABLE};
 __device__ __constant__ double2 c_twm[32] = {B200_TWIST_M_TABLE};
+
+// |Re| and |Im| of every W32^t = exp(-2 pi i t / 32) are among cos(pi k / 16), k = 1..7: ONE small table, so the seven
+// values stay in uniform registers for a whole transform.  (With the 16-entry complex table the compiler ran out of
+// uniform registers in the last butterfly stage and copied twiddles into the vector register file, which turns a
+// 2-cycle DFMA -- two vector-register operands -- into a 3-cycle one: tools/mb/pipes.cu.)
+__device__ __constant__ double c_cos16[8] = {1.0, 0x1.f6297cff75cb0p-1, 0x1.d906bcf328d46p-1, 0x1.a9b66290ea1a3p-1,
+                                             0x1.6a09e667f3bcdp-1, 0x1.1c73b39ae68c8p-1, 0x1.87de2a6aea963p-2, 0x1.8f8b83c69a60bp-3};
+// W32^t, t = 1..15, t != 8: re = cos(pi t / 16), im = -sin(pi t / 16)
+__device__ __forceinline__ double w32_re(const int t) { return t < 8 ? c_cos16[t] : -c_cos16[16 - t]; }
+__device__ __forceinline__ double w32_im(const int t) { return t < 8 ? -c_cos16[8 - t] : -c_cos16[t - 8]; }
 
 __host__ __device__ constexpr int brev5(int x) {
     return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
@@ -48,8 +57,8 @@ __device__ __forceinline__ void bfly(double &ar, double &ai, double &br, double 
         const double tr = ar - pr, ti = ai - pi;
         ar += pr; ai += pi; br = tr; bi = ti;
     } else {
-        const double wr = c_w32[tw].x;
-        const double wi = INV ? -c_w32[tw].y : c_w32[tw].y;
+        const double wr = w32_re(tw);
+        const double wi = INV ? -w32_im(tw) : w32_im(tw);
         double sr = fma(wr, br, ar);
         sr = fma(-wi, bi, sr);
         double si = fma(wr, bi, ai);
@@ -148,12 +157,13 @@ __device__ __forceinline__ void fwd1024(double (&xr)[32], double (&xi)[32], doub
 
 // Inverse transform (unnormalised; the 1/1024 is folded into the Fourier BSK).
 // In: x[brev5(k2)] = G[lane + 32*k2].  Out: x[m] = conj(A_l)-untwisted point l + 32*m; the caller
-// still has to multiply by conj(C_m).
+// still has to multiply by conj(C_m).  inv1024_pass1 touches registers only (the transposition buffer may still be
+// in use by the sibling warp); inv1024_rest needs the buffer.
+__device__ __forceinline__ void inv1024_pass1(double (&xr)[32], double (&xi)[32]) { fft32_dit<true>(xr, xi); }
 template <class TW>
-__device__ __forceinline__ void inv1024(double (&xr)[32], double (&xi)[32], double2 *tbuf, const TW &tw,
-                                        const int lane) {
+__device__ __forceinline__ void inv1024_rest(double (&xr)[32], double (&xi)[32], double2 *tbuf, const TW &tw,
+                                             const int lane) {
     uint32_t t0[16], t1[16];
-    fft32_dit<true>(xr, xi);
     tw.issue(0, t0);
 #pragma unroll
     for (int l = 0; l < 32; l++) tbuf[lane * kTStride + l] = make_double2(xr[l], xi[l]);
@@ -179,6 +189,12 @@ __device__ __forceinline__ void inv1024(double (&xr)[32], double (&xi)[32], doub
     }
     __syncwarp();
     fft32_dit<true>(xr, xi);
+}
+template <class TW>
+__device__ __forceinline__ void inv1024(double (&xr)[32], double (&xi)[32], double2 *tbuf, const TW &tw,
+                                        const int lane) {
+    inv1024_pass1(xr, xi);
+    inv1024_rest(xr, xi, tbuf, tw, lane);
 }
 
 // multiply register m by C_m (forward twist) / conj(C_m) (inverse untwist)

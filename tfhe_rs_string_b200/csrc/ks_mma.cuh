@@ -23,7 +23,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
-#include "pbs_kernel.cuh"   // mbarrier / bulk-copy helpers, tmem helpers
+#include "pbs_common.cuh"   // mbarrier / bulk-copy helpers, tmem helpers
 
 namespace b200 {
 

@@ -18,7 +18,7 @@
 //   * from_torus scales by 2^64 with an exponent add instead of a DMUL (the FP64 pipe is the
 //     binding resource).
 #pragma once
-#include "pbs_kernel.cuh"
+#include "pbs_common.cuh"
 
 namespace b200 {
 
@@ -71,7 +71,16 @@ __host__ __device__ constexpr size_t pbs3_smem_bytes() {
     return kPbsHeaderBytes + kBskSliceBytes + (size_t)kCts3 * pbs_ct_smem_bytes();
 }
 
-template <int kCts3>
+// kPhase: 0 = all warps in lock step; p > 0 (4 ciphertexts per CTA only) = the two halves of the CTA run one phase
+// apart: warps 4-7 (which share their SM sub-partitions with warps 0-3) start the gather of step i when warps 0-3
+// have finished theirs, and warps 0-3 start step i+1 when warps 4-7 have finished the inverse transform of step i.
+// Every phase of a CMUX step is bound by a different unit (gather: integer ALU + instruction fetch, transforms: FP64
+// pipe, exchange/multiply: shared memory, from_torus: conversion unit), so the two warps of a sub-partition then
+// always ask for different units.  Hand-over by named barriers 5 and 6 (bar.arrive / bar.sync, 256 threads).
+__device__ __forceinline__ void bar_arrive(const int id, const int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_sync_n(const int id, const int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int kCts3, int kPhase = 0>
 __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,6 +122,8 @@ __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
         tmem_wait_st();
     }
     const int n_act_cts = min(kCts3, a.batch - (int)blockIdx.x * kCts3);
+    const bool dephase = kPhase > 0 && kCts3 == 4 && n_act_cts == 4;   // CTA-uniform
+    const bool late = warp >= 4;
     const unsigned int n_act_warps = 2u * (unsigned int)n_act_cts;
     if (threadIdx.x == 0) issue_bsk_slice(bsk_s, a.bsk, 0, bsk_bar);
     tmem_fence_before();
@@ -124,7 +135,7 @@ __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
         const uint64_t *lwe = a.lwe_small + (size_t)ct * (a.n + 1);
         for (int i = p * 32 + lane; i < a.n; i += 64) ahat[i] = (uint16_t)modswitch2048(lwe[i]);
         const uint32_t bhat = modswitch2048(lwe[a.n]);
-        const uint64_t *lut = a.luts + ((size_t)(a.lut_idx ? a.lut_idx[ct] : 0u) * 2 + p) * kN;
+        const uint64_t *lut = a.luts + ((size_t)pbs_lut_id(a, ct) * 2 + p) * kN;
         // acc = LUT * X^-b~: polynomial_wrapping_monic_monomial_div (polynomial_algorithms.rs:315-354)
 #pragma unroll
         for (int c = 0; c < 8; c++) {
@@ -150,6 +161,10 @@ __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
         // Steps with a~ = 0 (mod 2N) are not skipped as the reference does (bootstrap.rs:281): the
         // rotation is then the identity, every digit is 0 and the step adds exactly zero.
         for (int i = 0; i < a.n; i++) {
+            if (dephase) {
+                if (late) bar_sync_n(5, 256);                  // wait until the early half has finished gather i
+                else if (i > 0) bar_sync_n(6, 256);            // wait until the late half has finished inverse transform i-1
+            }
             PBS3_TS(0);
             double xr[32], xi[32];
             // phase A: ct1 = acc * X^a~ - acc (polynomial_algorithms.rs:425-491), round + digit
@@ -189,6 +204,7 @@ __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
                 }
             }
             __syncwarp();  // all rotation reads done before the buffer is reused for the transposition
+            if (dephase && !late) bar_arrive(5, 256);
             PBS3_TS(1);
 
             fwd1024(xr, xi, tb_own, tw, lane);
@@ -232,11 +248,13 @@ __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
                 if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
                     issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
             }
-            ct_barrier(1 + ctl);   // the sibling has read this warp's transform before the buffer is reused
+            inv1024_pass1(zr, zi);   // registers only: runs under the sibling's reads of this warp's transform
+            ct_barrier(1 + ctl);     // the sibling has read this warp's transform before the buffer is reused
             PBS3_TS(8);
 
-            inv1024(zr, zi, tb_own, tw, lane);
+            inv1024_rest(zr, zi, tb_own, tw, lane);
             __syncwarp();  // transposition reads done before the rotation copy overwrites the buffer
+            if (dephase && late && i + 1 < a.n) bar_arrive(6, 256);
             PBS3_TS(9);
 
             // phase D: untwist, from_torus, wrapping add (fft/mod.rs:285-304), refresh both copies.

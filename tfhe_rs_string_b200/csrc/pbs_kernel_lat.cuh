@@ -132,7 +132,7 @@ __device__ __forceinline__ void lat_fwd_pass(const double (&xr)[16], const doubl
     for (int mm = 0; mm < 16; mm++) {
         double tr = fma(sgn, rr[mm], xr[mm]), ti = fma(sgn, ri[mm], xi[mm]);
         if (h && mm) {   // times -W32^mm (warp-uniform branch)
-            const double wr = -c_w32[mm].x, wi = -c_w32[mm].y;
+            const double wr = -w32_re(mm), wi = -w32_im(mm);
             const double nr = fma(-ti, wi, tr * wr);
             ti = fma(ti, wr, tr * wi);
             tr = nr;
@@ -151,7 +151,7 @@ __device__ __forceinline__ void lat_inv_pass(double (&xr)[16], double (&xi)[16],
     if (h) {
 #pragma unroll
         for (int mm = 1; mm < 16; mm++) {   // times conj(W32^mm)
-            const double wr = c_w32[mm].x, wi = -c_w32[mm].y;
+            const double wr = w32_re(mm), wi = -w32_im(mm);
             const double nr = fma(-xi[mm], wi, xr[mm] * wr);
             xi[mm] = fma(xi[mm], wr, xr[mm] * wi);
             xr[mm] = nr;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
         const uint64_t *lwe = a.lwe_small + (size_t)ct * (a.n + 1);
         for (int i = (p * 2 + h) * 32 + lane; i < a.n; i += 128) ahat[i] = (uint16_t)modswitch2048(lwe[i]);
         const uint32_t bhat = modswitch2048(lwe[a.n]);
-        const uint64_t *lut = a.luts + ((size_t)(a.lut_idx ? a.lut_idx[ct] : 0u) * 2 + p) * kN;
+        const uint64_t *lut = a.luts + ((size_t)pbs_lut_id(a, ct) * 2 + p) * kN;
         // acc = LUT * X^-b~ (polynomial_algorithms.rs:315-354); TMEM holds G = C - acc, shared memory r = -acc
 #pragma unroll
         for (int c = 0; c < 4; c++) {

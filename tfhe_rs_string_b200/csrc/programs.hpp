@@ -99,6 +99,14 @@ inline std::unique_ptr<Circuit> build_program(const std::string &op, const std::
     } else if (op == "string_contains" || op == "string_find") {
         need(4);
         const size_t n = shape[0], hl = shape[1], pl = shape[2], nb = shape[3];
+        if (op == "string_find") {
+            // the index (number of positions before the first match, hay_len - pat_len + 1 when absent) is a radix
+            // integer of nb blocks: it must not wrap
+            double cap = 1;
+            for (size_t k = 0; k < nb; k++) cap *= msg_mod;
+            if (pl <= hl && (double)(hl - pl + 1) >= cap)
+                throw std::invalid_argument("string_find: hay_len - pat_len + 1 does not fit the index radix (message_modulus^nb)");
+        }
         cp.reset(new Circuit(msg_mod, carry_mod, n * (hl + pl) * nb));
         Circuit &c = *cp;
         for (size_t s = 0; s < n; s++) {
@@ -132,6 +140,29 @@ inline std::unique_ptr<Circuit> build_program(const std::string &op, const std::
     }
     cp->finalize();
     return cp;
+}
+
+// How a named program's inputs / outputs decompose into independent units (shape[0] of them): used to shard a
+// program over several GPUs with no exchange between them (every integer / string of a batch is
+// independent).  Inputs are `in_seg.size()` consecutive arrays, array s holding units * in_seg[s] blocks.
+struct ProgramLayout {
+    bool splittable = false;
+    size_t units = 1;
+    std::vector<size_t> in_seg;
+    size_t out_per_unit = 0;
+};
+inline ProgramLayout program_layout(const std::string &op, const std::vector<uint64_t> &shape) {
+    ProgramLayout l;
+    auto at = [&](size_t i) { return i < shape.size() ? (size_t)shape[i] : (size_t)0; };
+    if (op == "radix_eq" || op == "radix_ne") { l = {true, at(0), {at(1), at(1)}, 1}; }
+    else if (op == "radix_add" || op == "radix_sub" || op == "radix_bitand" || op == "radix_bitor" || op == "radix_bitxor") { l = {true, at(0), {at(1), at(1)}, at(1)}; }
+    else if (op == "radix_shl") { l = {true, at(0), {at(1)}, at(1)}; }
+    else if (op.rfind("radix_scalar_", 0) == 0) { l = {true, at(0), {at(1)}, 1}; }
+    else if (op == "string_eq" || op == "string_ne" || op == "string_starts_with" || op == "string_ends_with") { l = {true, at(0), {at(1) * at(3), at(2) * at(3)}, 1}; }
+    else if (op == "string_to_uppercase" || op == "string_to_lowercase") { l = {true, at(0), {at(1) * at(2)}, at(1) * at(2)}; }
+    else if (op == "string_contains") { l = {true, at(0), {at(1) * at(3), at(2) * at(3)}, 1}; }
+    else if (op == "string_find") { l = {true, at(0), {at(1) * at(3), at(2) * at(3)}, 1 + at(3)}; }
+    return l;   // anything else (trivium, custom circuits): one unit, runs on the first GPU
 }
 
 }  // namespace b200

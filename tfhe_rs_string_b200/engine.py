@@ -9,22 +9,42 @@ _LIB = None
 
 # every symbol include/b200tfhe.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "b200tfhe_ctx_create", "b200tfhe_ctx_destroy", "b200tfhe_last_error", "b200tfhe_last_global_error",
+    "b200tfhe_ctx_create", "b200tfhe_ctx_create_multi", "b200tfhe_ctx_device_count", "b200tfhe_ctx_destroy", "b200tfhe_last_error", "b200tfhe_last_global_error",
     "b200tfhe_load_ksk", "b200tfhe_load_bsk_standard", "b200tfhe_key_arena", "b200tfhe_keys_adopt",
     "b200tfhe_register_lut", "b200tfhe_register_lut_from_table",
     "b200tfhe_keyswitch_batch", "b200tfhe_pbs_batch", "b200tfhe_ks_pbs_batch", "b200tfhe_pbs_ks_batch",
     "b200tfhe_keyswitch_batch_device", "b200tfhe_pbs_batch_device", "b200tfhe_ks_pbs_batch_device",
     "b200tfhe_pbs_ks_batch_device",
     "b200tfhe_lwe_linear_batch_device", "b200tfhe_sync", "b200tfhe_stream",
-    "b200tfhe_set_profiling", "b200tfhe_get_kernel_times", "b200tfhe_set_pbs_variant",
-    "b200tfhe_debug_negacyclic_mul",
-    "b200tfhe_program_create", "b200tfhe_program_info", "b200tfhe_program_run", "b200tfhe_program_run_device",
+    "b200tfhe_ks_pbs_batch_device_multi",
+    "b200tfhe_set_profiling", "b200tfhe_get_kernel_times", "b200tfhe_kernel_launch_count",
+    "b200tfhe_parse_server_key", "b200tfhe_load_server_key_bytes",
+    "b200tfhe_debug_negacyclic_mul", "b200tfhe_debug_pbs_steps",
+    "b200tfhe_program_create", "b200tfhe_program_create_from_circuit", "b200tfhe_program_info", "b200tfhe_program_run", "b200tfhe_program_run_device",
     "b200tfhe_program_destroy",
 ]
 
 
 class B200TfheError(RuntimeError):
     pass
+
+
+class KeyView(C.Structure):
+    """b200tfhe_key_view: where the key material sits inside a serialised server key."""
+    _fields_ = [
+        ("ksk_offset", C.c_uint64), ("ksk_len", C.c_uint64), ("bsk_offset", C.c_uint64), ("bsk_len", C.c_uint64),
+        ("bsk_poly_stride_bytes", C.c_uint64), ("bsk_is_fourier", C.c_uint32), ("pbs_order", C.c_uint32),
+        ("max_degree", C.c_uint64), ("max_noise_level", C.c_uint64),
+    ]
+
+
+class CircuitDesc(C.Structure):
+    """b200tfhe_circuit_desc: a caller-built level schedule (see include/b200tfhe.h)."""
+    _fields_ = [
+        ("n_inputs", C.c_size_t), ("n_nodes", C.c_size_t), ("n_luts", C.c_size_t), ("n_outputs", C.c_size_t),
+        ("node_term_begin", C.c_void_p), ("term_block", C.c_void_p), ("term_coeff", C.c_void_p),
+        ("node_plaintext", C.c_void_p), ("node_lut", C.c_void_p), ("luts", C.c_void_p), ("outputs", C.c_void_p),
+    ]
 
 
 class Params(C.Structure):
@@ -78,6 +98,14 @@ def load_library():
     ctx = C.c_void_p
     sig = {
         "b200tfhe_ctx_create": [C.POINTER(Params), C.c_int, C.POINTER(ctx)],
+        "b200tfhe_ctx_create_multi": [C.POINTER(Params), C.POINTER(C.c_int), C.c_int, C.POINTER(ctx)],
+        "b200tfhe_ctx_device_count": [ctx, C.POINTER(C.c_int)],
+        "b200tfhe_ks_pbs_batch_device_multi": [ctx, vp, vp, vp, vp],
+        "b200tfhe_kernel_launch_count": [ctx, C.POINTER(C.c_uint64)],
+        "b200tfhe_parse_server_key": [vp, C.c_size_t, C.POINTER(Params), C.POINTER(KeyView)],
+        "b200tfhe_load_server_key_bytes": [ctx, vp, C.c_size_t],
+        "b200tfhe_debug_pbs_steps": [ctx, u64p, u32p, u64p, C.c_size_t, C.c_uint32],
+        "b200tfhe_program_create_from_circuit": [ctx, C.POINTER(CircuitDesc), C.POINTER(C.c_void_p)],
         "b200tfhe_ctx_destroy": [ctx],
         "b200tfhe_last_error": [ctx, C.c_char_p, C.c_size_t],
         "b200tfhe_last_global_error": [C.c_char_p, C.c_size_t],
@@ -101,7 +129,6 @@ def load_library():
         "b200tfhe_set_profiling": [ctx, C.c_int],
         "b200tfhe_get_kernel_times": [ctx, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
                                       C.POINTER(C.c_uint64), C.c_int],
-        "b200tfhe_set_pbs_variant": [ctx, C.c_int],
         "b200tfhe_debug_negacyclic_mul": [ctx, u64p, u64p, u64p, C.c_size_t],
         "b200tfhe_program_create": [ctx, C.c_char_p, u64p, C.c_size_t, C.POINTER(C.c_void_p)],
         "b200tfhe_program_info": [C.c_void_p, u64p],
@@ -136,12 +163,15 @@ class Engine:
     """One context per GPU.  Mirrors the call surface of shortint::ServerKey for the KS+PBS path:
     keyswitch / programmable bootstrap / apply_lookup_table, batched."""
 
-    def __init__(self, params=None, device=0):
+    def __init__(self, params=None, device=0, devices=None):
+        """device: one GPU; devices=[...]: one context over several GPUs of the box (b200tfhe_ctx_create_multi)."""
         self.L = load_library()
         self.params = params or Params.message_2_carry_2()
-        self.device = device
+        self.devices = list(devices) if devices is not None else [device]
+        self.device = self.devices[0]
         h = C.c_void_p()
-        rc = self.L.b200tfhe_ctx_create(C.byref(self.params), device, C.byref(h))
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        rc = self.L.b200tfhe_ctx_create_multi(C.byref(self.params), devs, len(self.devices), C.byref(h))
         if rc != 0:
             buf = C.create_string_buffer(1024)
             self.L.b200tfhe_last_global_error(buf, 1024)
@@ -275,8 +305,31 @@ class Engine:
                                                      1 if reset else 0))
         return {"ks_ms": a.value, "ks_launches": na.value, "pbs_ms": b.value, "pbs_launches": nb.value}
 
-    def set_pbs_variant(self, v):
-        self._check(self.L.b200tfhe_set_pbs_variant(self.h, v))
+    def kernel_launch_count(self):
+        n = C.c_uint64()
+        self._check(self.L.b200tfhe_kernel_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def load_server_key_bytes(self, blob):
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        self._check(self.L.b200tfhe_load_server_key_bytes(self.h, buf.ctypes.data, buf.size))
+
+    def ks_pbs_batch_device_multi(self, d_ins, d_lut_ids, d_outs, batches):
+        """One device-resident shard per GPU of the context (lists of torch tensors / device addresses)."""
+        n = len(self.devices)
+        arr = lambda xs: (C.c_void_p * n)(*[_ptr(x) for x in xs])
+        a_in, a_out = arr(d_ins), arr(d_outs)
+        a_id = arr(d_lut_ids) if d_lut_ids is not None else None
+        a_b = (C.c_size_t * n)(*batches)
+        self._check(self.L.b200tfhe_ks_pbs_batch_device_multi(self.h, a_in, a_id, a_out, a_b))
+
+    def debug_pbs_steps(self, small_prefix, steps, lut_ids=None):
+        """The production PBS kernel stopped after `steps` CMUX steps; small_prefix: batch x (steps + 1)."""
+        cts = np.ascontiguousarray(small_prefix, dtype=np.uint64).reshape(-1, steps + 1)
+        ids = None if lut_ids is None else np.ascontiguousarray(lut_ids, dtype=np.uint32)
+        out = np.empty((cts.shape[0], self.params.big_lwe_size), dtype=np.uint64)
+        self._check(self.L.b200tfhe_debug_pbs_steps(self.h, _ptr(cts), _ptr(ids), _ptr(out), cts.shape[0], steps))
+        return out
 
     def debug_negacyclic_mul(self, a_int, b_torus, out):
         a = np.ascontiguousarray(a_int, dtype=np.uint64).reshape(-1, 2048)
@@ -286,20 +339,53 @@ class Engine:
         return out
 
 
+def parse_server_key(blob):
+    """b200tfhe_parse_server_key: (Params, KeyView) of a serialised server key; needs no GPU."""
+    L = load_library()
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    p, v = Params(), KeyView()
+    if L.b200tfhe_parse_server_key(buf.ctypes.data, buf.size, C.byref(p), C.byref(v)) != 0:
+        msg = C.create_string_buffer(1024)
+        L.b200tfhe_last_global_error(msg, 1024)
+        raise B200TfheError(msg.value.decode())
+    return p, v
+
+
 class Program:
     """A batched call site (radix / FheString / Trivium operation) compiled for one workload shape:
     b200tfhe_program_* in include/b200tfhe.h; names and shapes in csrc/programs.hpp."""
 
-    def __init__(self, engine, op, shape):
+    def __init__(self, engine, op, shape, _handle=None):
         self.engine = engine
         self.op, self.shape = op, list(shape)
-        sh = np.ascontiguousarray(shape, dtype=np.uint64)
         h = C.c_void_p()
-        engine._check(engine.L.b200tfhe_program_create(engine.h, op.encode(), _ptr(sh), len(sh), C.byref(h)))
+        if _handle is not None:
+            h = _handle
+        else:
+            sh = np.ascontiguousarray(shape, dtype=np.uint64)
+            engine._check(engine.L.b200tfhe_program_create(engine.h, op.encode(), _ptr(sh), len(sh), C.byref(h)))
         self.h = h
         info = np.zeros(6, dtype=np.uint64)
         engine._check(engine.L.b200tfhe_program_info(self.h, _ptr(info)))
         self.info = dict(zip(["n_inputs", "n_outputs", "n_pbs", "depth", "n_stages", "n_luts"], (int(x) for x in info)))
+
+    @classmethod
+    def from_circuit(cls, engine, n_inputs, nodes, luts, outputs):
+        """A caller-built schedule (b200tfhe_program_create_from_circuit).  nodes: list of
+        (terms=[(block, coeff), ...], plaintext, lut_index or -1); luts: list of function tables."""
+        tbeg, tb, tc, pt, nl = [0], [], [], [], []
+        for terms, plain, lut in nodes:
+            for b, c in terms:
+                tb.append(b); tc.append(c)
+            tbeg.append(len(tb)); pt.append(plain); nl.append(lut)
+        keep = [np.ascontiguousarray(tbeg, dtype=np.uint32), np.ascontiguousarray(tb, dtype=np.int32),
+                np.ascontiguousarray(tc, dtype=np.int64), np.ascontiguousarray(pt, dtype=np.uint64),
+                np.ascontiguousarray(nl, dtype=np.int32), np.ascontiguousarray(luts, dtype=np.uint64).ravel(),
+                np.ascontiguousarray(outputs, dtype=np.int32)]
+        d = CircuitDesc(n_inputs, len(nodes), len(luts), len(outputs), *[k.ctypes.data for k in keep])
+        h = C.c_void_p()
+        engine._check(engine.L.b200tfhe_program_create_from_circuit(engine.h, C.byref(d), C.byref(h)))
+        return cls(engine, "custom", [], _handle=h)
 
     def run(self, cts, out=None):
         """Host buffers (numpy or pinned torch): H2D, all levels, D2H; synchronous."""
