@@ -279,49 +279,70 @@ struct FftScratch {
 };
 static thread_local FftScratch tl_fft;
 
-/* fft/mod.rs:220-239 + 496-515: z_j = (i64(p_j) + i*i64(p_{j+N/2})) * w_j, then forward DFT */
-void forward_integer(const FftPlan &pl, double *out /*interleaved*/, const uint64_t *poly) {
-    const uint32_t n = pl.n;
-    tl_fft.ensure(n);
-    double *re = tl_fft.re.data(), *im = tl_fft.im.data();
+/* The conversion loops around the transforms, as separate functions so that they get the SIMD clones too
+ * (i64 <-> f64 conversions vectorise with AVX-512DQ; the reference does the same in fft/x86.rs:505+,823-874). */
+ORC_SIMD static void twist_in(double *__restrict re, double *__restrict im, const uint64_t *__restrict poly, const double *__restrict twr,
+                              const double *__restrict twi, uint32_t n, double scale) {
     for (uint32_t j = 0; j < n; j++) {
-        double a = (double)(int64_t)poly[j], b = (double)(int64_t)poly[j + n];
-        re[j] = a * pl.tw_re[j] - b * pl.tw_im[j];
-        im[j] = a * pl.tw_im[j] + b * pl.tw_re[j];
+        const double a = (double)(int64_t)poly[j] * scale, b = (double)(int64_t)poly[j + n] * scale;
+        re[j] = a * twr[j] - b * twi[j];
+        im[j] = a * twi[j] + b * twr[j];
     }
-    fft_forward(pl, re, im);
+}
+ORC_SIMD static void interleave(double *__restrict out, const double *__restrict re, const double *__restrict im, uint32_t n) {
     for (uint32_t j = 0; j < n; j++) { out[2 * j] = re[j]; out[2 * j + 1] = im[j]; }
+}
+ORC_SIMD static void deinterleave(double *__restrict re, double *__restrict im, const double *__restrict in, uint32_t n) {
+    for (uint32_t j = 0; j < n; j++) { re[j] = in[2 * j]; im[j] = in[2 * j + 1]; }
+}
+/* untwist, from_torus (same rounding and saturation as from_torus() above), wrapping add */
+ORC_SIMD static void untwist_add(uint64_t *__restrict poly, const double *__restrict re, const double *__restrict im, const double *__restrict twr,
+                                 const double *__restrict twi, uint32_t n, double norm) {
+    for (uint32_t half = 0; half < 2; half++) {
+        uint64_t *__restrict dst = poly + (size_t)half * n;
+        for (uint32_t j = 0; j < n; j++) {
+            const double wr = twr[j] * norm, wi = -twi[j] * norm;
+            const double v = half == 0 ? re[j] * wr - im[j] * wi : re[j] * wi + im[j] * wr;
+            double f = v - __builtin_nearbyint(v);
+            f = __builtin_nearbyint(f * 0x1p64);
+            const double c = f >= 0x1p63 ? 0.0 : f;                      /* keeps the conversion in range */
+            const int64_t s = f >= 0x1p63 ? INT64_MAX : (int64_t)c;     /* Rust `as i64` saturates (-2^63 converts exactly) */
+            dst[j] += (uint64_t)s;
+        }
+    }
+}
+
+/* Fourier-domain polynomials are kept SPLIT inside the oracle: n real parts, then n imaginary parts (the exported
+ * orc_fft_* test entry points convert to / from interleaved complex).
+ * fft/mod.rs:220-239 + 496-515: z_j = (i64(p_j) + i*i64(p_{j+N/2})) * w_j, then forward DFT */
+void forward_integer(const FftPlan &pl, double *out /*split*/, const uint64_t *poly) {
+    const uint32_t n = pl.n;
+    twist_in(out, out + n, poly, pl.tw_re.data(), pl.tw_im.data(), n, 1.0);
+    fft_forward(pl, out, out + n);
 }
 
 /* fft/mod.rs:197-218: same with inputs scaled by 2^-64 (key conversion) */
-void forward_torus(const FftPlan &pl, double *out, const uint64_t *poly) {
+void forward_torus(const FftPlan &pl, double *out /*split*/, const uint64_t *poly) {
     const uint32_t n = pl.n;
-    tl_fft.ensure(n);
-    double *re = tl_fft.re.data(), *im = tl_fft.im.data();
-    for (uint32_t j = 0; j < n; j++) {
-        double a = (double)(int64_t)poly[j] * 0x1p-64, b = (double)(int64_t)poly[j + n] * 0x1p-64;
-        re[j] = a * pl.tw_re[j] - b * pl.tw_im[j];
-        im[j] = a * pl.tw_im[j] + b * pl.tw_re[j];
-    }
-    fft_forward(pl, re, im);
-    for (uint32_t j = 0; j < n; j++) { out[2 * j] = re[j]; out[2 * j + 1] = im[j]; }
+    twist_in(out, out + n, poly, pl.tw_re.data(), pl.tw_im.data(), n, 0x1p-64);
+    fft_forward(pl, out, out + n);
 }
 
-/* fft/mod.rs:285-304 + 539-557: inverse DFT, times conj(w_j)/n, from_torus, wrapping add */
-void add_backward_torus(const FftPlan &pl, uint64_t *poly, const double *fourier) {
+/* fft/mod.rs:285-304 + 539-557: inverse DFT, times conj(w_j)/n, from_torus, wrapping add.  Destroys `fourier`. */
+void add_backward_torus(const FftPlan &pl, uint64_t *poly, double *fourier /*split*/) {
     const uint32_t n = pl.n;
-    tl_fft.ensure(n);
-    double *re = tl_fft.re.data(), *im = tl_fft.im.data();
-    for (uint32_t j = 0; j < n; j++) { re[j] = fourier[2 * j]; im[j] = fourier[2 * j + 1]; }
-    fft_inverse(pl, re, im);
-    const double norm = 1.0 / (double)n;
-    for (uint32_t j = 0; j < n; j++) {
-        double wr = pl.tw_re[j] * norm, wi = -pl.tw_im[j] * norm;
-        double tr = re[j] * wr - im[j] * wi;
-        double ti = re[j] * wi + im[j] * wr;
-        poly[j] += from_torus(tr);
-        poly[j + n] += from_torus(ti);
-    }
+    fft_inverse(pl, fourier, fourier + n);
+    untwist_add(poly, fourier, fourier + n, pl.tw_re.data(), pl.tw_im.data(), n, 1.0 / (double)n);
+}
+
+/* out (+)= a * b, pointwise complex on split polynomials (update_with_fmadd, ggsw.rs:616-697) */
+ORC_SIMD static void cmul_split(double *__restrict o, const double *__restrict a, const double *__restrict b, uint32_t n, bool accumulate) {
+    double *__restrict orr = o, *__restrict oi = o + n;
+    const double *__restrict ar = a, *__restrict ai = a + n, *__restrict br = b, *__restrict bi = b + n;
+    if (accumulate)
+        for (uint32_t q = 0; q < n; q++) { orr[q] += ar[q] * br[q] - ai[q] * bi[q]; oi[q] += ar[q] * bi[q] + ai[q] * br[q]; }
+    else
+        for (uint32_t q = 0; q < n; q++) { orr[q] = ar[q] * br[q] - ai[q] * bi[q]; oi[q] = ar[q] * bi[q] + ai[q] * br[q]; }
 }
 
 /* --------------------------------------------------------------------- integer primitives */
@@ -343,6 +364,20 @@ inline uint64_t decompose_one_level(uint32_t base_log, uint64_t &state, uint64_t
     carry >>= (base_log - 1);
     state += carry;
     return res - (carry << base_log);
+}
+
+/* TensorSignedDecompositionLendingIter (fft64/math/decomposition.rs:26-86) over whole polynomials, vectorised */
+ORC_SIMD static void init_states(uint64_t *__restrict st, const uint64_t *__restrict x, size_t len, uint32_t base_log, uint32_t level) {
+    const uint32_t shift = 64 - base_log * level - 1;
+    for (size_t j = 0; j < len; j++) st[j] = (((x[j] >> shift) + 1) & ~(uint64_t)1) << shift >> (shift + 1);
+}
+ORC_SIMD static void decompose_level(uint64_t *__restrict term, uint64_t *__restrict st, size_t len, uint32_t base_log, uint64_t mask) {
+    for (size_t j = 0; j < len; j++) {
+        const uint64_t res = st[j] & mask, hi = st[j] >> base_log;
+        const uint64_t carry = (((res - 1) | hi) & res) >> (base_log - 1);
+        st[j] = hi + carry;
+        term[j] = res - (carry << base_log);
+    }
 }
 
 /* fft_impl/common.rs:26-43 with offset 0, lut_count_log 0 */
@@ -559,13 +594,30 @@ void orc_monomial_mul_and_subtract(uint64_t *o, const uint64_t *i, size_t N, siz
 void orc_sample_extract0(uint64_t *lwe, const uint64_t *glwe, uint32_t k, uint32_t N) {
     sample_extract0(lwe, glwe, k, N);
 }
-void orc_fft_forward_integer(double *f, const uint64_t *poly, uint32_t N) { forward_integer(get_plan(N), f, poly); }
-void orc_fft_forward_torus(double *f, const uint64_t *poly, uint32_t N) { forward_torus(get_plan(N), f, poly); }
-void orc_fft_add_backward_torus(uint64_t *poly, const double *f, uint32_t N) { add_backward_torus(get_plan(N), poly, f); }
+void orc_fft_forward_integer(double *f, const uint64_t *poly, uint32_t N) {
+    std::vector<double> t(N);
+    forward_integer(get_plan(N), t.data(), poly);
+    interleave(f, t.data(), t.data() + N / 2, N / 2);
+}
+void orc_fft_forward_torus(double *f, const uint64_t *poly, uint32_t N) {
+    std::vector<double> t(N);
+    forward_torus(get_plan(N), t.data(), poly);
+    interleave(f, t.data(), t.data() + N / 2, N / 2);
+}
+void orc_fft_add_backward_torus(uint64_t *poly, const double *f, uint32_t N) {
+    std::vector<double> t(N);
+    deinterleave(t.data(), t.data() + N / 2, f, N / 2);
+    add_backward_torus(get_plan(N), poly, t.data());
+}
 uint64_t orc_from_torus(double x) { return from_torus(x); }
 
 /* ---------------------------------------------------------------------------- keyswitch */
 /* algorithms/lwe_keyswitch.rs:96-170 + slice_algorithms.rs:363-462 */
+/* slice_wrapping_sub_scalar_mul_assign, algorithms/slice_algorithms.rs:363-462 */
+ORC_SIMD static void sub_scalar_mul(uint64_t *__restrict out, const uint64_t *__restrict row, uint64_t d, uint32_t len) {
+    for (uint32_t j = 0; j < len; j++) out[j] -= row[j] * d;
+}
+
 void orc_keyswitch_raw(const uint64_t *ksk, uint32_t in_dim, uint32_t out_dim, uint32_t base_log,
                        uint32_t level, const uint64_t *in, uint64_t *out) {
     const uint32_t out_size = out_dim + 1;
@@ -577,7 +629,7 @@ void orc_keyswitch_raw(const uint64_t *ksk, uint32_t in_dim, uint32_t out_dim, u
         for (uint32_t li = 0; li < level; li++) {
             uint64_t d = decompose_one_level(base_log, state, mask);
             const uint64_t *row = ksk + ((size_t)i * level + li) * out_size;
-            for (uint32_t j = 0; j < out_size; j++) out[j] -= row[j] * d;
+            sub_scalar_mul(out, row, d, out_size);
         }
     }
 }
@@ -602,35 +654,19 @@ static void add_external_product(const orc_params &p, const FftPlan &pl, uint64_
     const size_t glwe_len = (size_t)(k + 1) * N;
     const uint64_t mask = ((uint64_t)1 << bl) - 1;
     /* TensorSignedDecompositionLendingIter::new (fft64/math/decomposition.rs:26-46) */
-    for (size_t j = 0; j < glwe_len; j++) s.states[j] = closest_representable(glwe[j], bl, lv) >> (64 - bl * lv);
+    init_states(s.states.data(), glwe, glwe_len, bl, lv);
     bool uninit = true;
     for (uint32_t li = 0; li < lv; li++) {
         /* levels come out l, l-1, ..., 1; GGSW level matrices are stored 1..l and iterated .rev() */
         uint32_t lvl = lv - li;
         const double *mat = ggsw_f + (size_t)(lvl - 1) * (k + 1) * (k + 1) * N; /* N doubles per poly */
         for (uint32_t row = 0; row <= k; row++) {
-            for (uint32_t j = 0; j < N; j++) s.term[j] = decompose_one_level(bl, s.states[(size_t)row * N + j], mask);
+            decompose_level(s.term.data(), &s.states[(size_t)row * N], N, bl, mask);
             forward_integer(pl, s.fourier.data(), s.term.data());
             const double *rowp = mat + (size_t)row * (k + 1) * N;
             /* update_with_fmadd, ggsw.rs:616-697: first write is a mul, later ones fused mul-add */
-            for (uint32_t col = 0; col <= k; col++) {
-                const double *l = rowp + (size_t)col * N;
-                double *o = &s.out_f[(size_t)col * N];
-                const double *f = s.fourier.data();
-                if (uninit) {
-                    for (uint32_t q = 0; q < N / 2; q++) {
-                        double lr = l[2 * q], lim = l[2 * q + 1], fr = f[2 * q], fi = f[2 * q + 1];
-                        o[2 * q] = lr * fr - lim * fi;
-                        o[2 * q + 1] = lr * fi + lim * fr;
-                    }
-                } else {
-                    for (uint32_t q = 0; q < N / 2; q++) {
-                        double lr = l[2 * q], lim = l[2 * q + 1], fr = f[2 * q], fi = f[2 * q + 1];
-                        o[2 * q] += lr * fr - lim * fi;
-                        o[2 * q + 1] += lr * fi + lim * fr;
-                    }
-                }
-            }
+            for (uint32_t col = 0; col <= k; col++)
+                cmul_split(&s.out_f[(size_t)col * N], rowp + (size_t)col * N, s.fourier.data(), N / 2, !uninit);
             uninit = false;
         }
     }

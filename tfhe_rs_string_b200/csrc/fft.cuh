@@ -29,15 +29,13 @@ constexpr int kTBufElems = 32 * kTStride;  // double2 elements per warp buffer (
 
 __device__ __constant__ double2 c_twm[32] = {B200_TWIST_M_TABLE};
 
-// |Re| and |Im| of every W32^t = exp(-2 pi i t / 32) are among cos(pi k / 16), k = 1..7: ONE small table, so the seven
-// values stay in uniform registers for a whole transform.  (With the 16-entry complex table the compiler ran out of
-// uniform registers in the last butterfly stage and copied twiddles into the vector register file, which turns a
-// 2-cycle DFMA -- two vector-register operands -- into a 3-cycle one: tools/mb/pipes.cu.)
-__device__ __constant__ double c_cos16[8] = {1.0, 0x1.f6297cff75cb0p-1, 0x1.d906bcf328d46p-1, 0x1.a9b66290ea1a3p-1,
-                                             0x1.6a09e667f3bcdp-1, 0x1.1c73b39ae68c8p-1, 0x1.87de2a6aea963p-2, 0x1.8f8b83c69a60bp-3};
-// W32^t, t = 1..15, t != 8: re = cos(pi t / 16), im = -sin(pi t / 16)
-__device__ __forceinline__ double w32_re(const int t) { return t < 8 ? c_cos16[t] : -c_cos16[16 - t]; }
-__device__ __forceinline__ double w32_im(const int t) { return t < 8 ? -c_cos16[8 - t] : -c_cos16[t - 8]; }
+// W32^t = exp(-2 pi i t / 32) in constant memory.  (Measured, tools/mb/pipes.cu: a DFMA with three distinct vector-register
+// operands takes 3 issue cycles on the FP64 pipe, one with a uniform-register / constant operand 2; a 7-value
+// deduplicated table was tried to keep every twiddle in uniform registers -- it cut the 3-operand DFMAs from 752 to 448
+// per CMUX step but cost 2.5x the spill traffic and no time, so the plain table stays.)
+__device__ __constant__ double2 c_w32[16] = {B200_W32_TABLE};
+__device__ __forceinline__ double w32_re(const int t) { return c_w32[t].x; }
+__device__ __forceinline__ double w32_im(const int t) { return c_w32[t].y; }
 
 __host__ __device__ constexpr int brev5(int x) {
     return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);

@@ -160,139 +160,21 @@ __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
         // ---------------------------------------------------------------- CMUX loop
         // Steps with a~ = 0 (mod 2N) are not skipped as the reference does (bootstrap.rs:281): the
         // rotation is then the identity, every digit is 0 and the step adds exactly zero.
-        for (int i = 0; i < a.n; i++) {
-            if (dephase) {
-                if (late) bar_sync_n(5, 256);                  // wait until the early half has finished gather i
-                else if (i > 0) bar_sync_n(6, 256);            // wait until the late half has finished inverse transform i-1
-            }
-            PBS3_TS(0);
-            double xr[32], xi[32];
-            // phase A: ct1 = acc * X^a~ - acc (polynomial_algorithms.rs:425-491), round + digit
-            // (ggsw.rs:514-521), exact int -> double, twist by C_m (fft/mod.rs:220-239)
-            {
-                const uint32_t ah = ahat[i];
-                const uint32_t base0 = (uint32_t)(lane + 4096 - (int)ah) & 4095u;   // source index of coefficient `lane`
-                const uint32_t base1 = (base0 + 1024u) & 4095u;                     // ... of coefficient `lane + 1024`
-                const uint32_t pos0 = base0 & 2047u, pos1 = base1 & 2047u;
-                // V = +acc_src when the source index is < N, -acc_src otherwise; with r = -acc stored:
-                // V = r ^ T - T with T = 0 (take r: source negated) or ~0 (take -r).
-                const uint32_t tn0 = (base0 & 2048u) ? 0u : 0xFFFFFFFFu, tn1 = (base1 & 2048u) ? 0u : 0xFFFFFFFFu;
-                const int mc0 = (int)((2048u - pos0 + 31u) >> 5), mc1 = (int)((2048u - pos1 + 31u) >> 5);  // first m past the wrap
-                const uint64_t *pn0 = rot + pos0, *pn1 = rot + pos1;
-                uint32_t h0[16], h1[16];
-                tmem_ld16_nc(t_acc, h0);
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    uint32_t(&h)[16] = (c & 1) ? h1 : h0;
-                    tmem_wait_ld16(h);
-                    if (c < 7) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
-#pragma unroll
-                    for (int mm = 0; mm < 4; mm++) {
-                        const int m = c * 4 + mm;
-                        const bool w0 = m >= mc0, w1 = m >= mc1;
-                        const uint64_t r0 = (w0 ? pn0 - kN : pn0)[32 * m], r1 = (w1 ? pn1 - kN : pn1)[32 * m];
-                        const uint32_t t0 = w0 ? ~tn0 : tn0, t1 = w1 ? ~tn1 : tn1;
-                        const uint64_t T0 = pack64(t0, t0), T1 = pack64(t1, t1);
-                        const uint64_t e0 = pack64(h[4 * mm], h[4 * mm + 1]) + (r0 ^ T0) - T0;
-                        const uint64_t e1 = pack64(h[4 * mm + 2], h[4 * mm + 3]) + (r1 ^ T1) - T1;
-                        // digit + (2^22 - 1) in [0, 2^23) -> double by exponent trick (exact)
-                        double fr = dbl((uint32_t)(e0 >> 41), 0x43300000u) - 4503599631564799.0;
-                        double fi = dbl((uint32_t)(e1 >> 41), 0x43300000u) - 4503599631564799.0;
-                        twist_m(fr, fi, m);
-                        xr[brev5(m)] = fr; xi[brev5(m)] = fi;
-                    }
-                }
-            }
-            __syncwarp();  // all rotation reads done before the buffer is reused for the transposition
-            if (dephase && !late) bar_arrive(5, 256);
-            PBS3_TS(1);
-
-            fwd1024(xr, xi, tb_own, tw, lane);
-            PBS3_TS(2);
-
-            // exchange the transforms; Out_p = B[p][p] * F_p + B[1-p][p] * F_{1-p}, written into the
-            // bit-reversed slot the inverse transform wants.  The own product needs nothing from the
-            // sibling, so it is formed before the barrier and hides the hand-over.
-#pragma unroll
-            for (int q = 0; q < 32; q++) tb_own[q * 32 + lane] = make_double2(xr[q], xi[q]);
-            PBS3_TS(3);
-            mbar_wait(bsk_bar, (uint32_t)(i & 1));
-            PBS3_TS(4);
-            double zr[32], zi[32];
-            {
-                const double2 *b_own = bsk_s + (size_t)(p * 2 + p) * kHalf + lane;         // row p, column p
-#pragma unroll
-                for (int q = 0; q < 32; q++) {
-                    const double2 bo = b_own[q * 32];
-                    zr[brev5(q)] = fma(-bo.y, xi[q], bo.x * xr[q]);
-                    zi[brev5(q)] = fma(bo.y, xr[q], bo.x * xi[q]);
-                }
-            }
-            PBS3_TS(5);
-            ct_barrier(1 + ctl);
-            PBS3_TS(6);
-            {
-                const double2 *b_oth = bsk_s + (size_t)((1 - p) * 2 + p) * kHalf + lane;   // row 1-p, column p
-#pragma unroll
-                for (int q = 0; q < 32; q++) {
-                    const double2 bx = b_oth[q * 32], g = tb_oth[q * 32 + lane];
-                    double o_r = fma(bx.x, g.x, zr[brev5(q)]), o_i = fma(bx.x, g.y, zi[brev5(q)]);
-                    zr[brev5(q)] = fma(-bx.y, g.y, o_r); zi[brev5(q)] = fma(bx.y, g.x, o_i);
-                }
-            }
-            PBS3_TS(7);
-            // this warp is done with the slice; the last of the CTA's warps refills the buffer
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned int old = atomicAdd(consumed, 1u);
-                if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
-                    issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
-            }
-            inv1024_pass1(zr, zi);   // registers only: runs under the sibling's reads of this warp's transform
-            ct_barrier(1 + ctl);     // the sibling has read this warp's transform before the buffer is reused
-            PBS3_TS(8);
-
-            inv1024_rest(zr, zi, tb_own, tw, lane);
-            __syncwarp();  // transposition reads done before the rotation copy overwrites the buffer
-            if (dephase && late && i + 1 < a.n) bar_arrive(6, 256);
-            PBS3_TS(9);
-
-            // phase D: untwist, from_torus, wrapping add (fft/mod.rs:285-304), refresh both copies.
-            // D1 converts all 64 values first (64 independent chains through the conversion unit, no
-            // ordering points in between), D2 then streams the accumulator through TMEM.
-            uint64_t dl0[32], dl1[32];
-#pragma unroll
-            for (int m = 0; m < 32; m++) {
-                double yr = zr[m], yi = zi[m];
-                untwist_m(yr, yi, m);
-                dl0[m] = from_torus_exp(yr); dl1[m] = from_torus_exp(yi);
-            }
-            {
-                uint32_t h0[16], h1[16];
-                tmem_ld16_nc(t_acc, h0);
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    uint32_t(&h)[16] = (c & 1) ? h1 : h0;
-                    tmem_wait_ld16(h);
-                    if (c < 7) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
-#pragma unroll
-                    for (int mm = 0; mm < 4; mm++) {
-                        const int m = c * 4 + mm;
-                        const int j = lane + 32 * m;
-                        // acc += delta  <=>  G -= delta, r = G - C
-                        const uint64_t g0 = pack64(h[4 * mm], h[4 * mm + 1]) - dl0[m];
-                        const uint64_t g1 = pack64(h[4 * mm + 2], h[4 * mm + 3]) - dl1[m];
-                        rot[j] = g0 - kAccC; rot[j + kHalf] = g1 - kAccC;
-                        h[4 * mm] = (uint32_t)g0; h[4 * mm + 1] = (uint32_t)(g0 >> 32);
-                        h[4 * mm + 2] = (uint32_t)g1; h[4 * mm + 3] = (uint32_t)(g1 >> 32);
-                    }
-                    tmem_st16_nc(t_acc + c * 16, h);
-                }
-                tmem_wait_st();
-            }
-            __syncwarp();  // rotation copy complete before the next step's gather
-            PBS3_TS(10);
+#ifdef B200TFHE_LAB_DUP_LOOP
+        // development experiment (tools/lab): the upper half of the CTA runs a second copy of the same loop, so the two
+        // warps of a sub-partition fetch different addresses while executing the same phases
+#if B200TFHE_LAB_DUP_LOOP == 2
+        if (p) {     // copies split by sub-partition parity: the two warps of a sub-partition share one copy
+#else
+        if (late) {  // copies split inside every sub-partition
+#endif
+#include "pbs_kernel3_loop.inc"
+        } else {
+#include "pbs_kernel3_loop.inc"
         }
+#else
+#include "pbs_kernel3_loop.inc"
+#endif
 
         // ---------------------------------------------------------------- sample extraction
         uint64_t *o = a.out + (size_t)ct * (kN + 1);
