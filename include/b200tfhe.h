@@ -204,6 +204,20 @@ int b200tfhe_program_run(b200tfhe_program *prog, const uint64_t *in, uint64_t *o
 int b200tfhe_program_run_device(b200tfhe_program *prog, const uint64_t *d_in, uint64_t *d_out);   /* device buffers, asynchronous */
 int b200tfhe_program_destroy(b200tfhe_program *prog);
 
+/* ---- boolean gates: 32-bit torus words (boolean/engine/{mod,bootstrapping}.rs) -------------------------------- */
+/* The reference's boolean layer keeps u32 ciphertexts and bootstraps every binary gate with a constant test polynomial
+ * (1/8).  `params`: BooleanParameters (boolean/parameters/mod.rs:123-192; message/carry modulus are ignored);
+ * keyswitch_first != 0 for EncryptionKeyChoice::Big sets (ciphertexts of k*N+1 words, keyswitch then bootstrap), 0 for
+ * ::Small (n+1 words, bootstrap then keyswitch).  One GPU per context; host buffers; synchronous. */
+typedef struct b200tfhe_boolean_ctx b200tfhe_boolean_ctx;
+int b200tfhe_boolean_ctx_create(const b200tfhe_params *params, int keyswitch_first, int device, b200tfhe_boolean_ctx **out);
+int b200tfhe_boolean_ctx_destroy(b200tfhe_boolean_ctx *ctx);
+int b200tfhe_boolean_last_error(const b200tfhe_boolean_ctx *ctx, char *buf, size_t buf_len);
+int b200tfhe_boolean_load_ksk(b200tfhe_boolean_ctx *ctx, const uint32_t *ksk, size_t n_u32);
+int b200tfhe_boolean_load_bsk_standard(b200tfhe_boolean_ctx *ctx, const uint32_t *bsk, size_t n_u32);
+/* gate: 0 AND, 1 NAND, 2 OR, 3 NOR, 4 XOR, 5 XNOR (boolean/engine/mod.rs:606-850), batched over independent pairs. */
+int b200tfhe_boolean_gate_batch(b200tfhe_boolean_ctx *ctx, int gate, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t batch);
+
 /* ---- unit-test hooks (exercise exactly the transforms the PBS kernel uses) ------------ */
 /* out[i] += a_int[i] (x) b_torus[i] in Z[X]/(X^2048+1); host buffers, count x 2048 u64 each.
  * Mirrors the reference's FFT product test, fft_impl/fft64/math/fft/tests.rs:82-222. */

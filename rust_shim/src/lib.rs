@@ -18,6 +18,10 @@ pub struct b200tfhe_ctx {
 pub struct b200tfhe_program {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct b200tfhe_boolean_ctx {
+    _private: [u8; 0],
+}
 
 /// `ClassicPBSParameters` (tfhe/src/shortint/parameters/mod.rs:62-76) flattened.
 #[repr(C)]
@@ -105,6 +109,14 @@ extern "C" {
     pub fn b200tfhe_load_server_key_bytes(ctx: *mut b200tfhe_ctx, bytes: *const u8, n_bytes: usize) -> c_int;
     pub fn b200tfhe_program_create_from_circuit(
         ctx: *mut b200tfhe_ctx, desc: *const b200tfhe_circuit_desc, out: *mut *mut b200tfhe_program,
+    ) -> c_int;
+    pub fn b200tfhe_boolean_ctx_create(params: *const b200tfhe_params, keyswitch_first: c_int, device: c_int, out: *mut *mut b200tfhe_boolean_ctx) -> c_int;
+    pub fn b200tfhe_boolean_ctx_destroy(ctx: *mut b200tfhe_boolean_ctx) -> c_int;
+    pub fn b200tfhe_boolean_last_error(ctx: *const b200tfhe_boolean_ctx, buf: *mut c_char, buf_len: usize) -> c_int;
+    pub fn b200tfhe_boolean_load_ksk(ctx: *mut b200tfhe_boolean_ctx, ksk: *const u32, n_u32: usize) -> c_int;
+    pub fn b200tfhe_boolean_load_bsk_standard(ctx: *mut b200tfhe_boolean_ctx, bsk: *const u32, n_u32: usize) -> c_int;
+    pub fn b200tfhe_boolean_gate_batch(
+        ctx: *mut b200tfhe_boolean_ctx, gate: c_int, a: *const u32, b: *const u32, out: *mut u32, batch: usize,
     ) -> c_int;
     pub fn b200tfhe_debug_pbs_steps(
         ctx: *mut b200tfhe_ctx, in_small: *const u64, lut_id: *const u32, out: *mut u64, batch: usize, steps: u32,

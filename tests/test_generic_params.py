@@ -75,7 +75,11 @@ def test_gpu_generic_kernel_matches_oracle(oracle_mod, name, batch):
         t0 = time.perf_counter()
         got = eng.ks_pbs_batch(cts, ids)
         dt = time.perf_counter() - t0
-        print(f"{name}: {batch} KS+PBS in {dt * 1e3:.1f} ms on the generic kernel")
+        t0 = time.perf_counter()
+        eng.ks_pbs_batch(cts[:1], ids[:1])
+        dt1 = time.perf_counter() - t0
+        print(f"{name}: {batch} KS+PBS in {dt * 1e3:.1f} ms, one KS+PBS in {dt1 * 1e3:.2f} ms on the generic kernel "
+              f"(reference CPU, 1 thread: {'7.28' if p.polynomial_size == 512 else '121'} ms, docs/getting_started/benchmarks.md:42)")
         ref = keys.ks_pbs_batch(cts, keys.lut(f))
         exp = [(f(int(m)) if m < ms else (2 * ms - f(int(m) - ms)) % (2 * ms)) for m in msgs]
         assert list(keys.decrypt_batch(got)) == exp

@@ -241,7 +241,7 @@ int launch_ks(b200tfhe_ctx *ctx, DevCtx &d, const uint64_t *d_in, uint64_t *d_ou
         KsMmaArgs m{};
         m.a_tiled = d.d_digits; m.b_tiled = ctx->d_ksk_limbs(d); m.in = d_in; m.out = d_out; m.g = g;
         m.batch = (int)batch; m.stages = ks_mma_pipeline_stages(g);
-        ks_mma_kernel<<<dim3(g.n_tiles, m_tiles), 128, ks_mma_smem_bytes(g), d.stream>>>(m);
+        ks_mma_kernel<<<dim3(m_tiles, g.n_tiles), 128, ks_mma_smem_bytes(g), d.stream>>>(m);
         d.kernel_launches += 2;
     } else {
         ks_generic_kernel<uint64_t><<<(unsigned)batch, 256, 0, d.stream>>>(d_in, ctx->d_ksk(d), d_out, (int)batch,
@@ -289,7 +289,9 @@ int launch_pbs(b200tfhe_ctx *ctx, DevCtx &d, const uint64_t *d_small, const uint
         g.base_log = (int)ctx->p.pbs_base_log; g.level = (int)ctx->p.pbs_level; g.fft_in_smem = ctx->fft_in_smem ? 1 : 0;
         g.n_luts = (uint32_t)d.lut_count; g.err_flag = d.d_err_flag;
         const size_t smem = ctx->fft_in_smem ? (size_t)ctx->p.polynomial_size / 2 * sizeof(double2) : 0;
-        pbs_generic_kernel<uint64_t><<<(unsigned)batch, 512, smem, d.stream>>>(g);
+        // one butterfly per thread and stage for small polynomials: a block barrier over 4 warps costs a third of one over 16
+        const unsigned threads = std::min(512u, std::max(128u, ctx->p.polynomial_size / 4));
+        pbs_generic_kernel<uint64_t><<<(unsigned)batch, threads, smem, d.stream>>>(g);
     }
     prof_end(d, d.ev_pbs);
     DEV_TRY(ctx, d, cudaGetLastError());
@@ -1325,3 +1327,5 @@ int b200tfhe_debug_pbs_steps(b200tfhe_ctx *ctx, const uint64_t *in_small, const 
 }
 
 }  // extern "C"
+
+#include "boolean_api.hpp"

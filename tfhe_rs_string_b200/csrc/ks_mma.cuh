@@ -173,7 +173,9 @@ struct KsMmaArgs {
 __global__ void __launch_bounds__(128, 1) ks_mma_kernel(const KsMmaArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nt = blockIdx.x, mt = blockIdx.y;
+    // consecutive CTAs share the KSK tile (nt) and differ in the ciphertext tile (mt): a wave of 148 CTAs then touches ~5 of the
+    // 24 KSK column tiles instead of all of them, so the 63 MB of limbs stream from HBM once per launch, not once per wave
+    const int mt = blockIdx.x, nt = blockIdx.y;
     const KsMmaGeom &g = a.g;
     const int S = a.stages, KS = g.k_stages;
     const uint32_t a_bytes = (uint32_t)g.a_stage_bytes(), b_bytes = (uint32_t)g.b_stage_bytes();
@@ -229,10 +231,12 @@ __global__ void __launch_bounds__(128, 1) ks_mma_kernel(const KsMmaArgs a) {
     __syncwarp();
     mbar_wait_parity(accum, 0);
     tmem_fence_after();
-    const int row = mt * kKmM + warp * 32 + lane;
+    // thread = one ciphertext (TMEM lane): recombine the 8 limbs of every output word, stage the warp's 32 x 32 word tile in
+    // shared memory (the pipeline buffers are idle by now: every MMA that read them has completed before `accum` fires) and
+    // write it out row by row, so that a warp stores 256 contiguous bytes per instruction instead of 32 words 743 words apart
+    const int row0 = mt * kKmM + warp * 32;
     const uint32_t t_row = tmem_d + (((uint32_t)warp * 32u) << 16);
-    const uint64_t body = row < a.batch ? a.in[(size_t)row * (g.n_in + 1) + g.n_in] : 0;
-    uint64_t *o = a.out + (size_t)row * g.out_size;
+    uint64_t *stage = reinterpret_cast<uint64_t *>(tiles) + (size_t)warp * 32 * 33;   // [32 rows][33]: padded against bank conflicts
 #pragma unroll 1
     for (int c4 = 0; c4 < kKmCols / 4; c4++) {
         uint32_t r[32];
@@ -243,8 +247,17 @@ __global__ void __launch_bounds__(128, 1) ks_mma_kernel(const KsMmaArgs a) {
             uint64_t v = 0;
 #pragma unroll
             for (int l = 0; l < 8; l++) v += (uint64_t)(int64_t)(int32_t)r[cc * 8 + l] << (8 * l);
-            const int col = nt * kKmCols + c4 * 4 + cc;
-            if (row < a.batch && col < g.out_size) o[col] = (col == g.out_size - 1 ? body : 0) - v;
+            stage[lane * 33 + c4 * 4 + cc] = v;
+        }
+    }
+    __syncwarp();
+    const int col = nt * kKmCols + lane;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; rr++) {
+        const int row = row0 + rr;
+        if (row < a.batch && col < g.out_size) {
+            const uint64_t body = col == g.out_size - 1 ? a.in[(size_t)row * (g.n_in + 1) + g.n_in] : 0;
+            a.out[(size_t)row * g.out_size + col] = body - stage[rr * 33 + lane];
         }
     }
 

@@ -19,6 +19,8 @@ EXPORTED_SYMBOLS = [
     "b200tfhe_ks_pbs_batch_device_multi",
     "b200tfhe_set_profiling", "b200tfhe_get_kernel_times", "b200tfhe_kernel_launch_count",
     "b200tfhe_parse_server_key", "b200tfhe_load_server_key_bytes",
+    "b200tfhe_boolean_ctx_create", "b200tfhe_boolean_ctx_destroy", "b200tfhe_boolean_last_error",
+    "b200tfhe_boolean_load_ksk", "b200tfhe_boolean_load_bsk_standard", "b200tfhe_boolean_gate_batch",
     "b200tfhe_debug_negacyclic_mul", "b200tfhe_debug_pbs_steps",
     "b200tfhe_program_create", "b200tfhe_program_create_from_circuit", "b200tfhe_program_info", "b200tfhe_program_run", "b200tfhe_program_run_device",
     "b200tfhe_program_destroy",
@@ -105,6 +107,12 @@ def load_library():
         "b200tfhe_parse_server_key": [vp, C.c_size_t, C.POINTER(Params), C.POINTER(KeyView)],
         "b200tfhe_load_server_key_bytes": [ctx, vp, C.c_size_t],
         "b200tfhe_debug_pbs_steps": [ctx, u64p, u32p, u64p, C.c_size_t, C.c_uint32],
+        "b200tfhe_boolean_ctx_create": [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(ctx)],
+        "b200tfhe_boolean_ctx_destroy": [ctx],
+        "b200tfhe_boolean_last_error": [ctx, C.c_char_p, C.c_size_t],
+        "b200tfhe_boolean_load_ksk": [ctx, vp, C.c_size_t],
+        "b200tfhe_boolean_load_bsk_standard": [ctx, vp, C.c_size_t],
+        "b200tfhe_boolean_gate_batch": [ctx, C.c_int, vp, vp, vp, C.c_size_t],
         "b200tfhe_program_create_from_circuit": [ctx, C.POINTER(CircuitDesc), C.POINTER(C.c_void_p)],
         "b200tfhe_ctx_destroy": [ctx],
         "b200tfhe_last_error": [ctx, C.c_char_p, C.c_size_t],
@@ -337,6 +345,54 @@ class Engine:
         assert out.dtype == np.uint64 and out.shape == a.shape and out.flags["C_CONTIGUOUS"]
         self._check(self.L.b200tfhe_debug_negacyclic_mul(self.h, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
         return out
+
+
+class BooleanEngine:
+    """The reference's u32 boolean gate path (boolean::ServerKey: and / nand / or / nor / xor / xnor) on one GPU."""
+    GATES = {"and": 0, "nand": 1, "or": 2, "nor": 3, "xor": 4, "xnor": 5}
+
+    def __init__(self, params, keyswitch_first, device=0):
+        self.L = load_library()
+        self.params, self.keyswitch_first = params, bool(keyswitch_first)
+        h = C.c_void_p()
+        if self.L.b200tfhe_boolean_ctx_create(C.byref(params), 1 if keyswitch_first else 0, device, C.byref(h)) != 0:
+            buf = C.create_string_buffer(1024)
+            self.L.b200tfhe_last_global_error(buf, 1024)
+            raise B200TfheError(buf.value.decode())
+        self.h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            buf = C.create_string_buffer(1024)
+            self.L.b200tfhe_boolean_last_error(self.h, buf, 1024)
+            raise B200TfheError(buf.value.decode())
+
+    def load_ksk(self, ksk):
+        k = np.ascontiguousarray(ksk, dtype=np.uint32)
+        self._check(self.L.b200tfhe_boolean_load_ksk(self.h, _ptr(k), k.size))
+
+    def load_bsk_standard(self, bsk):
+        b = np.ascontiguousarray(bsk, dtype=np.uint32)
+        self._check(self.L.b200tfhe_boolean_load_bsk_standard(self.h, _ptr(b), b.size))
+
+    def gate(self, gate, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        out = np.empty_like(a)
+        g = self.GATES[gate] if isinstance(gate, str) else gate
+        self._check(self.L.b200tfhe_boolean_gate_batch(self.h, g, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200tfhe_boolean_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def parse_server_key(blob):
