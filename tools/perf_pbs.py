@@ -6,7 +6,6 @@ import torch
 import tfhe_rs_string_b200 as T
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2]
 p = T.Params.message_2_carry_2()
 eng = T.Engine(p, 0)
 rng = np.random.default_rng(0)
@@ -19,8 +18,7 @@ d_out = torch.empty_like(d_in)
 d_ids = torch.full((B,), lid, dtype=torch.int32, device="cuda")
 torch.cuda.synchronize()
 eng.set_profiling(True)
-for v in variants:
-    eng.set_pbs_variant(v)
+for v in [3]:
     for _ in range(2):
         eng.ks_pbs_batch_device(d_in, d_ids, d_out, B)
     eng.sync(); eng.kernel_times(reset=True)
