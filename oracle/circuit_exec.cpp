@@ -43,24 +43,31 @@ int orc_circuit_run_cleartext(const char *op, const uint64_t *shape, size_t n_sh
                               const uint64_t *in_msgs, uint64_t *out_msgs) {
     try {
         auto c = build(op, shape, n_shape, mm, cm);
-        const uint64_t ms = (uint64_t)mm * cm, full = 2 * ms;
+        /* values are tracked in HALF message units modulo 4 * modulus_sup (the 16-input reductions of workloads.hpp use
+         * tables of +-1/2); a value entering a lookup, and every output, must be a whole number of units */
+        const uint64_t ms = (uint64_t)mm * cm, full = 4 * ms;
         std::vector<uint64_t> val(c->n_blocks());
-        for (size_t i = 0; i < c->n_inputs(); i++) val[i] = in_msgs[i] % full;
+        for (size_t i = 0; i < c->n_inputs(); i++) val[i] = (2 * in_msgs[i]) % full;
         for (size_t k = 0; k < c->nodes.size(); k++) {
             const Node &nd = c->nodes[k];
-            int64_t acc = (int64_t)nd.plaintext;
+            int64_t acc = 2 * (int64_t)nd.plaintext + (int64_t)nd.plaintext_half;
             for (uint32_t t = nd.term_begin; t < nd.term_end; t++) {
                 if (c->terms[t].block >= (int32_t)(c->n_inputs() + k)) throw std::logic_error("circuit not topologically ordered");
                 acc += c->terms[t].coeff * (int64_t)val[c->terms[t].block];
             }
             uint64_t v = (uint64_t)(((acc % (int64_t)full) + (int64_t)full) % (int64_t)full);
             if (nd.lut >= 0) {
-                const uint64_t y = c->luts[nd.lut][v % ms] % full;
-                v = v >= ms ? (full - y) % full : y;   /* negacyclic: padding bit set => -LUT */
+                if (v & 1) throw std::logic_error("lookup on a value that is off the message grid");
+                const uint64_t m = v / 2;                                  /* message incl. padding bit, < 2 * ms */
+                const uint64_t y = c->lut_entry_half_units(nd.lut, m % ms);
+                v = m >= ms ? (full - y) % full : y;   /* negacyclic: padding bit set => -LUT */
             }
             val[c->n_inputs() + k] = v;
         }
-        for (size_t i = 0; i < c->outputs.size(); i++) out_msgs[i] = val[c->outputs[i]];
+        for (size_t i = 0; i < c->outputs.size(); i++) {
+            if (val[c->outputs[i]] & 1) throw std::logic_error("program output is off the message grid");
+            out_msgs[i] = val[c->outputs[i]] / 2;
+        }
         return 0;
     } catch (const std::exception &e) { g_err = e.what(); return 1; }
 }
@@ -75,8 +82,11 @@ int orc_circuit_run_encrypted(const orc_keyset *ks, const char *op, const uint64
         const uint64_t ms = (uint64_t)p->message_modulus * p->carry_modulus;
         const uint64_t delta = ((uint64_t)1 << 63) / ms;
         const size_t glwe_len = (size_t)(p->glwe_dimension + 1) * p->polynomial_size;
-        std::vector<uint64_t> luts(c->luts.size() * glwe_len);
-        for (size_t l = 0; l < c->luts.size(); l++) orc_fill_accumulator(p, c->luts[l].data(), &luts[l * glwe_len]);
+        std::vector<uint64_t> luts(c->luts.size() * glwe_len, 0);
+        for (size_t l = 0; l < c->luts.size(); l++) {   /* mask polynomials zero, body as fill_accumulator builds it */
+            const std::vector<uint64_t> body = c->lut_body((int)l, p->polynomial_size);
+            std::memcpy(&luts[l * glwe_len + (size_t)p->glwe_dimension * p->polynomial_size], body.data(), body.size() * sizeof(uint64_t));
+        }
         std::vector<uint64_t> pool(c->n_blocks() * big);
         std::memcpy(pool.data(), in_cts, c->n_inputs() * big * sizeof(uint64_t));
         if (n_threads < 1) n_threads = 1;
@@ -91,7 +101,7 @@ int orc_circuit_run_encrypted(const orc_keyset *ks, const char *op, const uint64
                         const uint64_t cf = (uint64_t)c->terms[q].coeff;
                         for (size_t j = 0; j < big; j++) tmp[j] += cf * src[j];
                     }
-                    tmp[big - 1] += nd.plaintext * delta;
+                    tmp[big - 1] += nd.plaintext * delta + nd.plaintext_half * (delta / 2);
                     uint64_t *dst = &pool[(c->n_inputs() + k) * big];
                     if (nd.lut >= 0) orc_ks_pbs(ks, tmp.data(), &luts[(size_t)nd.lut * glwe_len], dst);
                     else std::memcpy(dst, tmp.data(), big * sizeof(uint64_t));

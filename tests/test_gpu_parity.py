@@ -142,9 +142,9 @@ def test_device_lut_id_out_of_range_is_reported(engine, real_keys):
 
 def test_pinned_and_pageable_host_buffers_agree(engine, real_keys):
     """ks_pbs_batch pipelines pinned buffers in place and stages pageable ones (numpy, Rust Vec<u64>) through the
-    context's pinned slabs; three chunks so that slab reuse is exercised."""
+    context's pinned slabs; five chunks of one wave each, so that the three slabs per direction are reused."""
     import torch
-    B = 1500
+    B = 2500
     msgs = np.arange(B) % 16
     cts = real_keys.encrypt_batch(msgs, seed=808)
     ids = np.full(B, engine.generate_lookup_table(lambda x: (x + 7) % 16), dtype=np.uint32)

@@ -155,7 +155,7 @@ def test_full_size_config3_256_strings_of_64_chars(engine, real_keys):
     for i in range(0, n, 2):   # half equal, half differing in one random position
         q = int(rng.integers(0, L)); b[i] = b[i][:q] + chr(32 + (ord(b[i][q]) - 31) % 95) + b[i][q + 1:]
     out, info = run(engine, real_keys, "string_eq", [n, L, L, 4], np.concatenate([chars(a).ravel(), chars(b).ravel()]), 710)
-    assert info["n_pbs"] == 83456
+    assert info["n_pbs"] == 69888 and info["depth"] == 3   # 256 x (256 block comparisons -> 16 -> 1)
     assert list(out) == [int(x == y) for x, y in zip(a, b)]
 
 

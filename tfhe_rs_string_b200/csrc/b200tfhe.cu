@@ -974,7 +974,7 @@ int part_upload(b200tfhe_ctx *ctx, ProgramPart &q, const std::vector<uint32_t> &
     for (size_t k = 0; k < c.nodes.size(); k++) {
         tbeg[k] = c.nodes[k].term_begin;
         nlut[k] = c.nodes[k].lut >= 0 ? lut_ids[c.nodes[k].lut] : 0;
-        npt[k] = c.nodes[k].plaintext * delta;
+        npt[k] = c.nodes[k].plaintext * delta + c.nodes[k].plaintext_half * (delta / 2);
     }
     tbeg[c.nodes.size()] = (uint32_t)c.terms.size();
     for (const Circuit::Stage &st : c.stages)
@@ -1037,8 +1037,14 @@ int program_finish(b200tfhe_ctx *ctx, b200tfhe_program *p) {
     for (ProgramPart &q : p->parts) {
         const Circuit &c = *q.c;
         std::vector<uint32_t> lut_ids(c.luts.size());
-        for (size_t l = 0; l < c.luts.size(); l++)
-            if (b200tfhe_register_lut_from_table(ctx, c.luts[l].data(), c.luts[l].size(), &lut_ids[l])) return 1;
+        for (size_t l = 0; l < c.luts.size(); l++) {
+            // whole-unit tables go through fill_accumulator on the library side; half-unit tables (the 16-input reductions) are
+            // built here with entries scaled by delta / 2
+            std::vector<uint64_t> acc(ctx->glwe_len(), 0);
+            const std::vector<uint64_t> body = c.lut_body((int)l, ctx->p.polynomial_size);
+            std::copy(body.begin(), body.end(), acc.begin() + (size_t)ctx->p.glwe_dimension * ctx->p.polynomial_size);
+            if (b200tfhe_register_lut(ctx, acc.data(), &lut_ids[l])) return 1;
+        }
         std::lock_guard<std::mutex> lk(ctx->mu);
         if (cudaSetDevice(ctx->devs[q.dev]->device) != cudaSuccess) return fail(ctx, "cudaSetDevice failed");
         const int rc = part_upload(ctx, q, lut_ids);

@@ -38,6 +38,10 @@ struct Term {
 struct Lin {
     std::vector<Term> terms;
     uint64_t cst = 0;
+    int64_t half = 0;      // additional constant in HALF message units (delta / 2): only the 16-input reductions of
+                           // workloads.hpp produce it
+    int64_t odd = 0;       // sum of the coefficients of blocks that hold an odd number of half units (outputs of half-unit
+                           // tables); the value is a whole number of units iff half + odd is even
     uint32_t level = 0;    // dependency level of the deepest block referenced
     uint32_t degree = 0;   // upper bound of the encrypted value (reference: Degree bookkeeping)
     bool is_const() const { return terms.empty(); }
@@ -47,6 +51,7 @@ struct Lin {
 struct Node {
     uint32_t term_begin = 0, term_end = 0;  // into Circuit::terms
     uint64_t plaintext = 0;                 // message units, added to the body
+    uint64_t plaintext_half = 0;            // plus this many half units (delta / 2), modulo 4 * modulus_sup
     int32_t lut = -1;                       // index into Circuit::luts, -1 = linear only (no PBS)
     uint32_t level = 0;
 };
@@ -86,6 +91,13 @@ class Circuit {
         r.degree = a.degree + (uint32_t)(m > 0 ? m : 0);
         return r;
     }
+    // a + h * delta / 2 (leveled): undoes the -1/2 offset of a half-unit lookup table (lut_half)
+    Lin add_half(const Lin &a, int64_t h, uint32_t degree) const {
+        Lin r = a;
+        r.half += h;
+        r.degree = degree;
+        return r;
+    }
     Lin axpy(const Lin &a, int64_t ca, const Lin &b, int64_t cb) const {
         std::map<int32_t, int64_t> acc;
         for (const Term &t : a.terms) acc[t.block] += t.coeff * ca;
@@ -96,6 +108,8 @@ class Circuit {
         const int64_t mod = 2 * (int64_t)modulus_sup();
         int64_t c = ((int64_t)a.cst * ca + (int64_t)b.cst * cb) % mod;
         r.cst = (uint64_t)((c + mod) % mod);
+        r.half = a.half * ca + b.half * cb;
+        r.odd = a.odd * ca + b.odd * cb;
         r.level = std::max(a.level, b.level);
         r.degree = a.degree * (uint32_t)(ca < 0 ? -ca : ca) + b.degree * (uint32_t)(cb < 0 ? -cb : cb);
         return r;
@@ -111,6 +125,40 @@ class Circuit {
         luts.push_back(table);
         lut_index_[table] = id;
         return id;
+    }
+    // A table whose entries are in HALF message units (delta / 2), possibly negative.  The negacyclic rule LUT(x + modulus_sup)
+    // = -LUT(x) makes a lookup on the 17 values 0..modulus_sup well defined only for outputs symmetric around 0; a table
+    // of +-1/2 followed by add_half(+1) is how a PBS tests a sum of modulus_sup boolean flags (one more than the
+    // reference's are_all_comparisons_block_true can take, scalar_comparison.rs:161-183), see workloads.hpp all_true.
+    int lut_half(const std::function<int64_t(uint64_t)> &f) {
+        std::vector<uint64_t> table(modulus_sup());
+        const uint64_t mod = 4 * (uint64_t)modulus_sup();
+        for (uint32_t x = 0; x < modulus_sup(); x++) table[x] = (uint64_t)(((f(x) % (int64_t)mod) + (int64_t)mod) % (int64_t)mod) | kHalfTag;
+        auto it = lut_index_.find(table);
+        if (it != lut_index_.end()) return it->second;
+        const int id = (int)luts.size();
+        luts.push_back(table);
+        lut_index_[table] = id;
+        return id;
+    }
+    // entries of a half-unit table carry this tag bit so that equal numbers in different units stay different tables
+    static constexpr uint64_t kHalfTag = (uint64_t)1 << 62;
+    bool lut_is_half(int id) const { return !luts[id].empty() && (luts[id][0] & kHalfTag) != 0; }
+    // entry x of table id in half units modulo 4 * modulus_sup (whole-unit tables: twice the entry)
+    uint64_t lut_entry_half_units(int id, uint64_t x) const {
+        const uint64_t e = luts[id][x], mod = 4 * (uint64_t)modulus_sup();
+        return lut_is_half(id) ? (e & ~kHalfTag) % mod : (2 * e) % mod;
+    }
+    // GLWE body of table id (fill_accumulator, shortint/engine/mod.rs:92-127) with entries scaled by delta or delta / 2
+    std::vector<uint64_t> lut_body(int id, uint32_t polynomial_size) const {
+        const size_t ms = modulus_sup(), box = polynomial_size / ms, half_box = box / 2;
+        const uint64_t half_delta = ((uint64_t)1 << 62) / ms;
+        std::vector<uint64_t> body(polynomial_size);
+        for (size_t i = 0; i < ms; i++)
+            for (size_t j = 0; j < box; j++) body[i * box + j] = lut_entry_half_units(id, i) * half_delta;
+        for (size_t j = 0; j < half_box; j++) body[j] = 0 - body[j];
+        std::rotate(body.begin(), body.begin() + half_box, body.end());
+        return body;
     }
     // generate_lookup_table_bivariate_with_factor, shortint/server_key/bivariate_pbs.rs:71-98
     int lut_bivariate(const std::function<uint64_t(uint64_t, uint64_t)> &f, uint32_t factor) {
@@ -131,12 +179,21 @@ class Circuit {
     }
     Lin pbs_unchecked(const Lin &x, int lut_id) {
         uint64_t mx = 0;
-        for (uint64_t v : luts.at(lut_id)) mx = std::max(mx, v);
+        if (!lut_is_half(lut_id))
+            for (uint64_t v : luts.at(lut_id)) mx = std::max(mx, v);
         return pbs_unchecked(x, lut_id, (uint32_t)mx);
     }
     Lin pbs_unchecked(const Lin &x, int lut_id, uint32_t out_degree) {
         if (lut_id < 0 || lut_id >= (int)luts.size()) throw std::out_of_range("lut id");
+        if ((x.half + x.odd) & 1) throw std::logic_error("pbs: operand is off the message grid by half a unit");
+        if (x.is_const() && x.half != 0) {   // an even number of half units is a whole number of units
+            Lin y = add_const(x, x.half / 2);
+            y.half = 0;
+            y.degree = x.degree;
+            return pbs_unchecked(y, lut_id, out_degree);
+        }
         if (x.is_const()) {
+            if (lut_is_half(lut_id)) throw std::logic_error("pbs: half-unit table on a constant operand");
             // trivial_pbs_assign: value = body / delta; negate the table entry when the padding bit is set
             const uint64_t ms = modulus_sup();
             const uint64_t v = x.cst % (2 * ms);
@@ -147,6 +204,7 @@ class Circuit {
         r.terms.push_back({new_node(x, lut_id), 1});
         r.level = x.level + 1;
         r.degree = out_degree;
+        r.odd = lut_is_half(lut_id) ? 1 : 0;   // +-1/2 tables leave an odd number of half units in the block
         return r;
     }
     Lin pbs(const Lin &x, int lut_id) {
@@ -161,13 +219,14 @@ class Circuit {
 
     // A block that physically holds x (needed for outputs); no PBS.
     Lin materialize(const Lin &x) {
-        if (x.is_plain_block()) return x;
+        if (x.is_plain_block() && x.half == 0 && x.odd == 0) return x;
         Lin r;
         r.terms.push_back({new_node(x, -1), 1});
         // the node itself runs right after the level that produced its operands (stage key 2L+1);
         // anything that consumes the materialised block is scheduled from the next level on
         r.level = x.level + 1;
         r.degree = x.degree;
+        r.odd = (x.half + x.odd) & 1;
         return r;
     }
     // like materialize, but always a fresh block (a caller-built schedule addresses nodes by position)
@@ -260,6 +319,8 @@ class Circuit {
         for (const Term &t : x.terms) terms.push_back(t);
         nd.term_end = (uint32_t)terms.size();
         nd.plaintext = x.cst;
+        const int64_t hm = 4 * (int64_t)modulus_sup();
+        nd.plaintext_half = (uint64_t)(((x.half % hm) + hm) % hm);
         nd.lut = lut_id;
         nd.level = lut_id >= 0 ? x.level + 1 : x.level;
         nodes.push_back(nd);

@@ -33,35 +33,46 @@ inline Lin bool_xor(Circuit &c, const Lin &a, const Lin &b) {
 }
 inline Lin bool_not(Circuit &c, const Lin &a) { return c.add_const(c.scale(a, -1), 1); }   // boolean_bitnot: 1 - x, leveled
 
-// are_all_comparisons_block_true, src/integer/server_key/radix_parallel/scalar_comparison.rs:147-192
+// are_all_comparisons_block_true, src/integer/server_key/radix_parallel/scalar_comparison.rs:147-192.  The reference sums
+// modulus_sup - 1 = 15 flags per lookup (x == 15).  A full chunk here takes modulus_sup = 16: the sum 0..16 reaches the
+// padding bit exactly at "all true", where the negacyclic lookup returns -LUT(0); with the constant table -1/2 the PBS yields
+// -delta/2 below 16 and +delta/2 at 16, and adding delta/2 (leveled) gives the flag.  256 block comparisons reduce in two
+// levels (256 -> 16 -> 1) instead of three, which is one bootstrap depth less for every string comparison.
 inline Lin all_true(Circuit &c, std::vector<Lin> flags) {
     if (flags.empty()) return c.constant(1);
-    const size_t max_value = c.modulus_sup() - 1;
+    const size_t ms = c.modulus_sup();
     while (flags.size() > 1) {
         std::vector<Lin> next;
-        for (size_t i = 0; i < flags.size(); i += max_value) {
-            const size_t n = std::min(max_value, flags.size() - i);
+        for (size_t i = 0; i < flags.size(); i += ms) {
+            const size_t n = std::min(ms, flags.size() - i);
             Lin sum = flags[i];
             for (size_t j = 1; j < n; j++) sum = c.add(sum, flags[i + j]);
-            next.push_back(c.pbs(sum, c.lut([n](uint64_t x) { return (uint64_t)(x == n); })));
+            if (n == ms)
+                next.push_back(c.add_half(c.pbs_unchecked(sum, c.lut_half([](uint64_t) { return (int64_t)-1; }), 1), 1, 1));
+            else
+                next.push_back(c.pbs(sum, c.lut([n](uint64_t x) { return (uint64_t)(x == n); })));
         }
         flags.swap(next);
     }
     return flags[0];
 }
-// is_at_least_one_comparisons_block_true, scalar_comparison.rs:194-228
+// is_at_least_one_comparisons_block_true, scalar_comparison.rs:194-228; full chunks of 16 with the table
+// (-1/2 at 0, +1/2 elsewhere): the sum 16 reads -LUT(0) = +1/2 as it must
 inline Lin any_true(Circuit &c, std::vector<Lin> flags) {
     if (flags.empty()) return c.constant(0);
-    const size_t max_value = c.modulus_sup() - 1;
+    const size_t ms = c.modulus_sup();
     bool first = true;
     while (flags.size() > 1 || first) {
         first = false;
         std::vector<Lin> next;
-        for (size_t i = 0; i < flags.size(); i += max_value) {
-            const size_t n = std::min(max_value, flags.size() - i);
+        for (size_t i = 0; i < flags.size(); i += ms) {
+            const size_t n = std::min(ms, flags.size() - i);
             Lin sum = flags[i];
             for (size_t j = 1; j < n; j++) sum = c.add(sum, flags[i + j]);
-            next.push_back(n == 1 ? sum : c.pbs(sum, c.lut([](uint64_t x) { return (uint64_t)(x != 0); })));
+            if (n == ms)
+                next.push_back(c.add_half(c.pbs_unchecked(sum, c.lut_half([](uint64_t x) { return (int64_t)(x == 0 ? -1 : 1); }), 1), 1, 1));
+            else
+                next.push_back(n == 1 ? sum : c.pbs(sum, c.lut([](uint64_t x) { return (uint64_t)(x != 0); })));
         }
         flags.swap(next);
     }
@@ -118,11 +129,14 @@ inline Radix radix_sub(Circuit &c, Radix a, Radix b) {
     return r;
 }
 
-// unchecked_eq_parallelized, radix_parallel/comparison.rs:10-33
-inline Lin radix_eq(Circuit &c, const Radix &a, const Radix &b) {
+// unchecked_eq_parallelized, radix_parallel/comparison.rs:10-33: block `==` flags (one bivariate PBS each), then all-true
+inline void radix_eq_flags(Circuit &c, const Radix &a, const Radix &b, std::vector<Lin> &out) {
     const int lut = c.lut_bivariate([](uint64_t x, uint64_t y) { return (uint64_t)(x == y); }, c.msg_mod);
-    std::vector<Lin> cmp(a.size());
-    for (size_t i = 0; i < a.size(); i++) cmp[i] = c.pbs_bivariate(a[i], b[i], lut, c.msg_mod);
+    for (size_t i = 0; i < a.size(); i++) out.push_back(c.pbs_bivariate(a[i], b[i], lut, c.msg_mod));
+}
+inline Lin radix_eq(Circuit &c, const Radix &a, const Radix &b) {
+    std::vector<Lin> cmp;
+    radix_eq_flags(c, a, b, cmp);
     return all_true(c, cmp);
 }
 
@@ -281,8 +295,8 @@ inline Radix to_lowercase_char(Circuit &c, const Radix &ch) {
 // reference becomes one sum-of-flags tree over all character comparisons
 inline Lin string_eq(Circuit &c, const FheChars &a, const FheChars &b) {
     const size_t n = std::min(a.size(), b.size());
-    std::vector<Lin> flags;
-    for (size_t i = 0; i < n; i++) flags.push_back(radix_eq(c, a[i], b[i]));
+    std::vector<Lin> flags;   // block comparisons of ALL characters in one reduction tree
+    for (size_t i = 0; i < n; i++) radix_eq_flags(c, a[i], b[i], flags);
     if (a.size() != b.size()) {   // the longer string must continue with a padding zero (:195-212)
         const FheChars &longer = a.size() > b.size() ? a : b;
         flags.push_back(scalar_eq(c, longer[n], 0));
@@ -293,14 +307,14 @@ inline Lin string_eq(Circuit &c, const FheChars &a, const FheChars &b) {
 inline Lin match_at(Circuit &c, const FheChars &hay, const FheChars &pat, size_t pos) {
     if (pat.size() > hay.size() - pos) return c.constant(0);
     std::vector<Lin> flags;
-    for (size_t j = 0; j < pat.size(); j++) flags.push_back(radix_eq(c, hay[pos + j], pat[j]));
+    for (size_t j = 0; j < pat.size(); j++) radix_eq_flags(c, hay[pos + j], pat[j], flags);
     return all_true(c, flags);
 }
 // starts_with_encrypted_vec with Padding::None (contains.rs:96-134): the overlapping characters agree and,
 // when the prefix is longer than the string, its next character is a padding zero
 inline Lin string_starts_with(Circuit &c, const FheChars &s, const FheChars &prefix) {
     std::vector<Lin> flags;
-    for (size_t j = 0; j < std::min(s.size(), prefix.size()); j++) flags.push_back(radix_eq(c, s[j], prefix[j]));
+    for (size_t j = 0; j < std::min(s.size(), prefix.size()); j++) radix_eq_flags(c, s[j], prefix[j], flags);
     if (prefix.size() > s.size()) flags.push_back(scalar_eq(c, prefix[s.size()], 0));
     return all_true(c, flags);
 }
