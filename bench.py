@@ -139,6 +139,11 @@ def cpu_baseline(sample, threads, cap):
     out = keys.ks_pbs_batch(cts, lut, n_threads=threads)
     dt = time.perf_counter() - t0
     ok = bool((keys.decrypt_batch(out) == (np.arange(sample) % 16)).all())
+    # one thread alone (no contention for memory bandwidth / sibling hyperthreads): the figure to hold against the
+    # reference's published 16.6 ms per ciphertext on one m6i.metal core
+    t0 = time.perf_counter()
+    keys.ks_pbs_batch(cts[:4], lut, n_threads=1)
+    cpu_baseline.single_thread_ms = (time.perf_counter() - t0) / 4 * 1e3
     return sample / dt, dt, ok, sample
 
 
@@ -443,6 +448,7 @@ def run_b200(args):
             v, dt, ok, sample = cpu_baseline(args.cpu_sample, threads_all, B)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads_all, "kind": "port",
                                     "ms_per_ciphertext_per_thread": 1e3 * threads_all / v,
+                                    "ms_per_ciphertext_one_thread_alone": getattr(cpu_baseline, "single_thread_ms", None),
                                     "sample": f"{sample} of the {B} ciphertexts, identity LUT, {dt:.1f} s on {threads_all} host threads, decrypt ok={ok}; "
                                               "reference's published figure: 16.6 ms per ciphertext per thread (AVX-512, m6i.metal)"}
         print(json.dumps(line))

@@ -288,9 +288,9 @@ int launch_pbs(b200tfhe_ctx *ctx, DevCtx &d, const uint64_t *d_small, const uint
         g.batch = (int)batch; g.n = (int)ctx->p.lwe_dimension; g.k = (int)ctx->p.glwe_dimension; g.log2N = ctx->log2N;
         g.base_log = (int)ctx->p.pbs_base_log; g.level = (int)ctx->p.pbs_level; g.fft_in_smem = ctx->fft_in_smem ? 1 : 0;
         g.n_luts = (uint32_t)d.lut_count; g.err_flag = d.d_err_flag;
-        const size_t smem = ctx->fft_in_smem ? (size_t)ctx->p.polynomial_size / 2 * sizeof(double2) : 0;
+        const size_t smem = ctx->fft_in_smem ? (size_t)ctx->p.polynomial_size * 3 / 4 * sizeof(double2) : 0;   // buffer + roots
         // one butterfly per thread and stage for small polynomials: a block barrier over 4 warps costs a third of one over 16
-        const unsigned threads = std::min(512u, std::max(128u, ctx->p.polynomial_size / 4));
+        const unsigned threads = std::min(1024u, std::max(128u, ctx->p.polynomial_size / 4));
         pbs_generic_kernel<uint64_t><<<(unsigned)batch, threads, smem, d.stream>>>(g);
     }
     prof_end(d, d.ev_pbs);
@@ -496,7 +496,7 @@ int b200tfhe_ctx_create_multi(const b200tfhe_params *params, const int *devices,
     ctx->fast_path = fast;
     ctx->ks_tensor = ks_tensor;
     ctx->log2N = (int)log2N;
-    ctx->fft_in_smem = (size_t)p.polynomial_size / 2 * sizeof(double2) <= 160 * 1024;
+    ctx->fft_in_smem = (size_t)p.polynomial_size * 3 / 4 * sizeof(double2) <= 200 * 1024;   // N/2 points + N/4 roots: N <= 16384
     ctx->ks_geom = geom;
     ctx->off_bsk = 0;
     ctx->off_ksk = align_up(ctx->bsk_len() / 2 * sizeof(double2), 256);  // N/2 complex per polynomial

@@ -185,7 +185,7 @@ int b200tfhe_boolean_gate_batch(b200tfhe_boolean_ctx *ctx, int gate, const uint3
     g.lut_idx = nullptr; g.luts = ctx->d_lut; g.bsk = ctx->d_bsk; g.roots = ctx->d_roots; g.twist = ctx->d_twist;
     g.acc_ws = ctx->d_acc; g.fourier_ws = ctx->d_fourier; g.batch = (int)batch; g.n = (int)p.lwe_dimension; g.k = (int)p.glwe_dimension;
     g.log2N = ctx->log2N; g.base_log = (int)p.pbs_base_log; g.level = (int)p.pbs_level; g.fft_in_smem = 1; g.n_luts = 1; g.err_flag = nullptr;
-    const size_t smem = (size_t)p.polynomial_size / 2 * sizeof(double2);
+    const size_t smem = (size_t)p.polynomial_size * 3 / 4 * sizeof(double2);   // FFT buffer + roots of unity
     const int n_in = (int)(p.glwe_dimension * p.polynomial_size);
     const unsigned threads = std::min(512u, std::max(128u, p.polynomial_size / 4));
     if (ctx->ks_first) {

@@ -110,7 +110,7 @@ __device__ __forceinline__ Torus gen_from_torus(const double x) {      // torus/
 }
 
 template <typename Torus>
-__global__ void __launch_bounds__(512, 1) pbs_generic_kernel(const GenPbsArgs a) {
+__global__ void __launch_bounds__(1024, 1) pbs_generic_kernel(const GenPbsArgs a) {
     extern __shared__ __align__(16) unsigned char gen_smem[];
     constexpr int bits = TorusTraits<Torus>::bits;
     const int ct = blockIdx.x;
@@ -128,6 +128,15 @@ __global__ void __launch_bounds__(512, 1) pbs_generic_kernel(const GenPbsArgs a)
     double2 *outf = a.fourier_ws + (size_t)ct * n_f * half;
     double2 *buf = a.fft_in_smem ? reinterpret_cast<double2 *>(gen_smem) : outf + (size_t)k1 * half;
     const int ms_shift = bits - a.log2N - 2;                             // fast_pbs_modulus_switch, common.rs:26-43
+    // the N/4 roots of unity are read with power-of-two strides by every butterfly: keep them next to the buffer in shared
+    // memory (a strided global load per butterfly was most of the time of a CMUX step for N = 8192)
+    const double2 *roots = a.roots;
+    if (a.fft_in_smem) {
+        double2 *rs = reinterpret_cast<double2 *>(gen_smem) + half;
+        for (int t = threadIdx.x; t < (N >> 2); t += blockDim.x) rs[t] = a.roots[t];
+        roots = rs;
+        __syncthreads();
+    }
 
     // acc = LUT * X^-b~ (polynomial_wrapping_monic_monomial_div, polynomial_algorithms.rs:315-354)
     const int bhat = (int)((((lwe[a.n] >> ms_shift) + 1) >> 1));
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(512, 1) pbs_generic_kernel(const GenPbsArgs a)
                     const double d1 = gen_digit<Torus>(v1, a.base_log, a.level, lvl);
                     buf[j] = gen_cmul(make_double2(d0, d1), a.twist[j]);
                 }
-                gen_fft_forward(buf, a.roots, half);
+                gen_fft_forward(buf, roots, half);
                 const double2 *bk = a.bsk + ((((size_t)i * a.level + (lvl - 1)) * k1 + r) * k1) * half;
                 for (int c = 0; c < k1; c++) {
                     const double2 *b = bk + (size_t)c * half;
@@ -171,7 +180,7 @@ __global__ void __launch_bounds__(512, 1) pbs_generic_kernel(const GenPbsArgs a)
         for (int c = 0; c < k1; c++) {
             const double2 *o = outf + (size_t)c * half;
             for (int f = threadIdx.x; f < half; f += blockDim.x) buf[f] = o[f];
-            gen_fft_inverse(buf, a.roots, half);
+            gen_fft_inverse(buf, roots, half);
             Torus *ac = acc + (size_t)c * N;
             for (int j = threadIdx.x; j < half; j += blockDim.x) {
                 const double2 tw = a.twist[j];
