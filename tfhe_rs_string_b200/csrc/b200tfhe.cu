@@ -19,7 +19,7 @@
 #include "lwe_linear.cuh"
 #include "pbs_common.cuh"
 #include "pbs_generic.cuh"
-#include "pbs_kernel3.cuh"
+#include "pbs_kernel5.cuh"
 #include "pbs_kernel_lat.cuh"
 #include "programs.hpp"
 #include "key_import.hpp"
@@ -98,8 +98,8 @@ int configure_device_once(int device) {
     auto set = [&](const void *fn, int bytes) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     };
-    set((const void *)pbs_kernel3<3>, (int)pbs3_smem_bytes<3>());
-    set((const void *)pbs_kernel3<4>, (int)pbs3_smem_bytes<4>());
+    set((const void *)pbs_kernel5<3>, (int)pbs5_smem_bytes<3>());
+    set((const void *)pbs_kernel5<4>, (int)pbs5_smem_bytes<4>());
     set((const void *)pbs_lat_kernel<1>, (int)pbs_lat_smem_bytes<1>());
     set((const void *)pbs_lat_kernel<2>, (int)pbs_lat_smem_bytes<2>());
     // parameter-independent maxima: two live contexts with different keyswitch levels share these functions
@@ -265,8 +265,8 @@ void launch_pbs_fast(DevCtx &d, const PbsArgs &a) {
     switch ((int)per_cta) {
         case 1: pbs_lat_kernel<1><<<(unsigned)a.batch, 256, pbs_lat_smem_bytes<1>(), d.stream>>>(a); break;
         case 2: pbs_lat_kernel<2><<<(unsigned)((a.batch + 1) / 2), 256, pbs_lat_smem_bytes<2>(), d.stream>>>(a); break;
-        case 3: pbs_kernel3<3><<<(unsigned)((a.batch + 2) / 3), 192, pbs3_smem_bytes<3>(), d.stream>>>(a); break;
-        default: pbs_kernel3<4><<<(unsigned)((a.batch + 3) / 4), 256, pbs3_smem_bytes<4>(), d.stream>>>(a); break;
+        case 3: pbs_kernel5<3><<<(unsigned)((a.batch + 2) / 3), 192, pbs5_smem_bytes<3>(), d.stream>>>(a); break;
+        default: pbs_kernel5<4><<<(unsigned)((a.batch + 3) / 4), 256, pbs5_smem_bytes<4>(), d.stream>>>(a); break;
     }
 }
 

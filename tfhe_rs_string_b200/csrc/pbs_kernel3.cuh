@@ -54,6 +54,11 @@ __device__ __forceinline__ void undbl(const double d, uint32_t &lo, uint32_t &hi
 __device__ __forceinline__ uint64_t from_torus_exp(const double x) {
     const double f = x - rint(x);
     const double s = __hiloint2double(__double2hiint(f) + (64 << 20), __double2loint(f));
+#ifdef B200TFHE_LAB_NOSAT
+    // development (tools/lab): a fractional part of exactly +1/2 gives 2^63 instead of the saturated 2^63 - 1, so that
+    // pbs_kernel5 (whose from_torus does not saturate) can be compared bit for bit
+    if (s == 9223372036854775808.0) return 0x8000000000000000ull;
+#endif
     return (uint64_t)__double2ll_rn(s);
 }
 
@@ -63,6 +68,13 @@ __device__ __forceinline__ uint64_t from_torus_exp(const double x) {
 #define PBS3_TS(k) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && i >= 100 && i < 108) a.dbg[((i - 100) * 8 + warp) * 16 + (k)] = clock64(); } while (0)
 #else
 #define PBS3_TS(k) do { } while (0)
+#endif
+// Development aid (tools/lab): compile with -DB200TFHE_DUMP to record, for CTA 0 and the last CMUX step, every lane's digits,
+// inverse-transform outputs and torus increments into PbsArgs::dbg ([warp][m][lane][6]).
+#ifdef B200TFHE_DUMP
+#define PBS_DUMP(k, v) do { if (a.dbg && blockIdx.x == 0 && i == a.n - 1) a.dbg[(((size_t)warp * 32 + m) * 32 + lane) * 6 + (k)] = (long long)(v); } while (0)
+#else
+#define PBS_DUMP(k, v) do { } while (0)
 #endif
 // kCts3 ciphertexts per CTA: 4 for throughput; 1..3 for small batches (fewer warps per SM sub-partition
 // shorten the per-step critical path, see launch_pbs3), always one CTA per SM.

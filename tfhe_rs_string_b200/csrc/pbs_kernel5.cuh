@@ -1,0 +1,407 @@
+// pbs_kernel5.cuh -- fourth generation of the batched programmable bootstrap for k = 1, N = 2048, one level of
+// base 2^23 (same contract, data layouts and reference citations as pbs_kernel3.cuh; one warp per GLWE polynomial,
+// kCts ciphertexts per CTA, one CTA per SM).  What changed against pbs_kernel3 (measured there: every phase of a CMUX
+// step is bound by ONE unit that both warps of an SM sub-partition want at the same time -- gather: instruction
+// issue, transforms: FP64 pipe, exchange: shared memory + pair barriers, from_torus: the conversion unit):
+//
+//   * Accumulator convention G = -acc, the same 64-bit word in TMEM (home layout) and in the shared-memory rotation
+//     copy; the rounding/bias constant C = 2^63 - 2^40 of the exact digit (decomposer.rs:98-116, iter.rs:120-127) is an
+//     immediate of the high-word add:  digit + (2^22 - 1) = hi32(G_own +- G_src + C) >> 9.
+//   * Rotated gather with NO per-element wrap or sign test.  The rotation copy carries an overflow zone of 8 slots
+//     (256 words holding the negated first 256 coefficients).  A lane's 64 slots are visited in 8 groups of 8; for a
+//     group the source indices of all 32 lanes lie in a window of 256 + 31 consecutive coefficients of the
+//     4096-periodic negacyclic extension, so ONE warp-uniform (segment, offset) pair serves the whole group: the
+//     address is base + immediate and the sign is one mask per group (polynomial_algorithms.rs:425-491).
+//   * from_torus without the conversion unit (FRND / F2I are 13-cycle instructions here): two exponent-aligned
+//     additions split x into its top 14 fractional bits and an exact remainder (torus/mod.rs:72-78; round-half-even
+//     like fft/x86.rs:864; bit-identical to rint + cvt.rni except that a fractional part of exactly +1/2 gives 2^63
+//     instead of the saturated 2^63 - 1).
+//   * The two warps of a ciphertext write their transforms INTO EACH OTHER'S buffer, so no warp ever waits for the
+//     sibling to finish reading: the two pair barriers of a step are split arrive / wait mbarriers whose arrive sits
+//     a full 32-point transform before the matching wait.
+#pragma once
+#include "pbs_kernel3.cuh"
+
+namespace b200 {
+
+constexpr int kZone5 = 256;                                   // overflow zone of the rotation copy (words)
+constexpr int kBuf5Bytes = (kN + kZone5) * 8;                 // 18,432 B per warp: rotation copy / transposition / sibling's transform
+constexpr int kHdr5Bytes = 128;                               // tmem slot @0, BSK mbarrier @8, consumer counter @16, pair mbarriers @32
+constexpr uint64_t kFtBias = 0x4338000000000000ull;           // bit pattern of 1.5 * 2^52
+static_assert(kBuf5Bytes >= kTBufElems * (int)sizeof(double2), "transposition buffer must fit");
+
+template <int kCts>
+__host__ __device__ constexpr size_t pbs5_smem_bytes() {
+    return kHdr5Bytes + kBskSliceBytes + (size_t)kCts * (2 * kBuf5Bytes + kMaxSmallDim * sizeof(uint16_t));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// from_torus on the FP64 pipe only.  |x| < 2^37.  Returns d with  round_half_even(x * 2^64) mod 2^64 = d - kFtBias.
+//   t = x + 1.5*2^38 has ulp 2^-14: its low mantissa word holds round(x * 2^14);  l = x - (t - 1.5*2^38) is exact,
+//   |l| <= 2^-15;  u = l * 2^64 + 1.5*2^52 holds round_half_even(l * 2^64) as a 52-bit two's complement mantissa.
+__device__ __forceinline__ uint64_t from_torus_fp(const double x) {
+    const double t = x + 412316860416.0;                       // 1.5 * 2^38
+    const double l = x - (t - 412316860416.0);
+    const double u = fma(l, 18446744073709551616.0, 6755399441055744.0);
+    return pack64((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u) + ((uint32_t)__double2loint(t) << 18));
+}
+
+// Development switches (tools/lab): bit 0 = last stage of the forward transform fused with the hand-over and the own
+// product; bit 1 = sibling product at the leaves of a depth-first inverse first pass.
+#ifndef PBS5_FUSE
+#define PBS5_FUSE 0
+#endif
+
+// stages [kFirst, kLast] (butterfly distance 2^stage) of the in-register 32-point DIT transform of fft.cuh
+template <bool INV, int kFirst, int kLast>
+__device__ __forceinline__ void fft32_dit_stages(double (&xr)[32], double (&xi)[32]) {
+#pragma unroll
+    for (int half = 1 << kFirst; half <= (1 << kLast); half <<= 1) {
+#pragma unroll
+        for (int base = 0; base < 32; base += 2 * half) {
+#pragma unroll
+            for (int t = 0; t < half; t++)
+                bfly<INV>(xr[base + t], xi[base + t], xr[base + t + half], xi[base + t + half], t * (16 / half));
+        }
+    }
+}
+// the same butterflies in depth-first order; leaf(r, xr, xi) produces register r (bit-reversed input order) just before
+// its first use.  (The arrays are passed down explicitly: a lambda capturing them by reference sends them to local memory.)
+template <bool INV, int kLo, int kLen, class Leaf>
+__device__ __forceinline__ void fft32_dit_df(double (&xr)[32], double (&xi)[32], const Leaf &leaf) {
+    if constexpr (kLen == 1) {
+        leaf.template run<kLo>(xr, xi);
+    } else {
+        fft32_dit_df<INV, kLo, kLen / 2>(xr, xi, leaf);
+        fft32_dit_df<INV, kLo + kLen / 2, kLen / 2>(xr, xi, leaf);
+#pragma unroll
+        for (int t = 0; t < kLen / 2; t++)
+            bfly<INV>(xr[kLo + t], xi[kLo + t], xr[kLo + t + kLen / 2], xi[kLo + t + kLen / 2], t * (32 / kLen));
+    }
+}
+// z[r] += B[1-p][p][q] * F_sibling[q] for the frequency block q = brev5(r) that register r of the inverse transform holds
+struct SiblingProduct {
+    const double2 *b_oth, *f_oth;   // both already offset by the lane
+    template <int kR>
+    __device__ __forceinline__ void run(double (&zr)[32], double (&zi)[32]) const {
+        constexpr int q = brev5(kR);
+        const double2 bx = b_oth[q * 32], g = f_oth[q * 32];
+        const double o_r = fma(bx.x, g.x, zr[kR]), o_i = fma(bx.x, g.y, zi[kR]);
+        zr[kR] = fma(-bx.y, g.y, o_r); zi[kR] = fma(bx.y, g.x, o_i);
+    }
+};
+template <int kR>
+__device__ __forceinline__ void sibling_products(double (&zr)[32], double (&zi)[32], const SiblingProduct &oth) {
+    if constexpr (kR < 32) {
+        oth.template run<kR>(zr, zi);
+        sibling_products<kR + 1>(zr, zi, oth);
+    }
+}
+template <int kQ>
+__device__ __forceinline__ void own_product(double (&zr)[32], double (&zi)[32], const double (&xr)[32], const double (&xi)[32],
+                                            const double2 *b_own, double2 *f_dst) {
+    f_dst[kQ * 32] = make_double2(xr[kQ], xi[kQ]);
+    const double2 bo = b_own[kQ * 32];
+    zr[brev5(kQ)] = fma(-bo.y, xi[kQ], bo.x * xr[kQ]);
+    zi[brev5(kQ)] = fma(bo.y, xr[kQ], bo.x * xi[kQ]);
+}
+template <int kQ, bool kFused>
+__device__ __forceinline__ void own_products(double (&zr)[32], double (&zi)[32], double (&xr)[32], double (&xi)[32],
+                                             const double2 *b_own, double2 *f_dst) {
+    if constexpr (kFused) {
+        if constexpr (kQ < 16) {
+            bfly<false>(xr[kQ], xi[kQ], xr[kQ + 16], xi[kQ + 16], kQ);   // last stage: outputs kQ and kQ + 16 are final
+            own_product<kQ>(zr, zi, xr, xi, b_own, f_dst);
+            own_product<kQ + 16>(zr, zi, xr, xi, b_own, f_dst);
+            own_products<kQ + 1, kFused>(zr, zi, xr, xi, b_own, f_dst);
+        }
+    } else {
+        if constexpr (kQ < 32) {
+            own_product<kQ>(zr, zi, xr, xi, b_own, f_dst);
+            own_products<kQ + 1, kFused>(zr, zi, xr, xi, b_own, f_dst);
+        }
+    }
+}
+
+#ifdef B200TFHE_TIMELINE
+#define PBS5_TS(k) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && i >= 100 && i < 108) a.dbg[((i - 100) * 8 + warp) * 16 + (k)] = clock64(); } while (0)
+#else
+#define PBS5_TS(k) do { } while (0)
+#endif
+
+template <int kCts>
+__global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ctl = warp >> 1, p = warp & 1;
+    const int ct = blockIdx.x * kCts + ctl;
+    const bool active = ct < a.batch;
+
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem);
+    uint64_t *bsk_bar = reinterpret_cast<uint64_t *>(smem + 8);
+    unsigned int *consumed = reinterpret_cast<unsigned int *>(smem + 16);
+    uint64_t *bar_free = reinterpret_cast<uint64_t *>(smem + 32) + 2 * ctl;   // both warps are done reading their own buffer
+    uint64_t *bar_full = bar_free + 1;                                        // both warps have written their transform
+    double2 *bsk_s = reinterpret_cast<double2 *>(smem + kHdr5Bytes);
+    unsigned char *ctbase = smem + kHdr5Bytes + kBskSliceBytes + (size_t)ctl * (2 * kBuf5Bytes + kMaxSmallDim * sizeof(uint16_t));
+    double2 *tb_own = reinterpret_cast<double2 *>(ctbase + (size_t)p * kBuf5Bytes);
+    double2 *tb_sib = reinterpret_cast<double2 *>(ctbase + (size_t)(1 - p) * kBuf5Bytes);
+    uint16_t *ahat = reinterpret_cast<uint16_t *>(ctbase + (size_t)2 * kBuf5Bytes);
+    uint64_t *rot = reinterpret_cast<uint64_t *>(tb_own);   // rotation copy (G = -acc, + overflow zone) aliases the transposition buffer
+
+    // ---------------------------------------------------------------- CTA setup
+    constexpr uint32_t kTmemCols = kCts <= 2 ? 256u : 512u;   // twiddles + 128 accumulator columns per warp of a quadrant
+    if (warp == 0) tmem_alloc(slot, kTmemCols);
+    if (threadIdx.x == 0) {
+        mbar_init(bsk_bar, 1);
+        *consumed = 0;
+    }
+    if (lane == 0 && p == 0) {
+        mbar_init(bar_free, 2);
+        mbar_init(bar_full, 2);
+    }
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t tbase = *slot;
+    const uint32_t tquad = tbase + (((uint32_t)(warp & 3) * 32u) << 16);
+    const uint32_t t_acc = tquad + kTmemAcc0 + (uint32_t)(warp >> 2) * 128u;
+    const TmemTwiddles tw{tquad};
+    if (warp < 4) {   // one warp per TMEM quadrant stores its lanes' twiddle columns
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint32_t r[16];
+            GlobalTwiddles{a.twid, lane}.issue(c, r);
+            tmem_st16(tquad + c * 16, r);
+        }
+        tmem_wait_st();
+    }
+    const int n_act_cts = min(kCts, a.batch - (int)blockIdx.x * kCts);
+    const unsigned int n_act_warps = 2u * (unsigned int)n_act_cts;
+    if (threadIdx.x == 0) issue_bsk_slice(bsk_s, a.bsk, 0, bsk_bar);
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+
+    if (active) {
+        // ---------------------------------------------------------------- prologue
+        const uint64_t *lwe = a.lwe_small + (size_t)ct * (a.n + 1);
+        for (int i = p * 32 + lane; i < a.n; i += 64) ahat[i] = (uint16_t)modswitch2048(lwe[i]);
+        const uint32_t bhat = modswitch2048(lwe[a.n]);
+        const uint64_t *lut = a.luts + ((size_t)pbs_lut_id(a, ct) * 2 + p) * kN;
+        // acc = LUT * X^-b~: polynomial_wrapping_monic_monomial_div (polynomial_algorithms.rs:315-354); stored as G = -acc
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint32_t h[16];
+#pragma unroll
+            for (int mm = 0; mm < 4; mm++) {
+                const int j = lane + 32 * (c * 4 + mm);
+                const uint32_t i0 = (uint32_t)(j + bhat) & 4095u, i1 = (i0 + 1024u) & 4095u;
+                uint64_t v0 = lut[i0 & 2047u], v1 = lut[i1 & 2047u];
+                if (i0 & 2048u) v0 = 0 - v0;
+                if (i1 & 2048u) v1 = 0 - v1;
+                const uint64_t g0 = 0 - v0, g1 = 0 - v1;
+                rot[j] = g0; rot[j + kHalf] = g1;
+                if (c < 2) rot[kN + j] = v0;
+                h[4 * mm] = (uint32_t)g0; h[4 * mm + 1] = (uint32_t)(g0 >> 32);
+                h[4 * mm + 2] = (uint32_t)g1; h[4 * mm + 3] = (uint32_t)(g1 >> 32);
+            }
+            tmem_st16(t_acc + c * 16, h);
+        }
+        tmem_wait_st();
+        ct_barrier(1 + ctl);  // a~ table visible to both warps; rotation copy visible within the warp
+
+        // ---------------------------------------------------------------- CMUX loop
+        // Steps with a~ = 0 (mod 2N) are not skipped as the reference does (bootstrap.rs:281): the rotation is then the
+        // identity, every digit is 0 and the step adds exactly zero.
+        for (int i = 0; i < a.n; i++) {
+            const uint32_t par = (uint32_t)(i & 1);
+            PBS5_TS(0);
+            double xr[32], xi[32];
+            // phase A: ct1 = acc * X^a~ - acc, round + digit (ggsw.rs:514-521), exact int -> double, twist by C_m
+            {
+                const uint32_t q0 = (4096u - (uint32_t)ahat[i]) & 4095u;   // source index (in the 4096-periodic extension) of coefficient 0
+                const uint64_t *lanebase = rot + lane;
+                const uint64_t *pr = lanebase, *pi = lanebase;
+                uint32_t tr = 0, ti = 0;
+                uint32_t h0[16], h1[16];
+                tmem_ld16_nc(t_acc, h0);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t(&h)[16] = (c & 1) ? h1 : h0;
+                    tmem_wait_ld16(h);
+                    if (c < 7) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
+                    if ((c & 1) == 0) {
+                        // group (c >> 1) of the first half and of the second half (1024 coefficients further on): one
+                        // segment / offset for all lanes and all 8 slots of the group.  Stored word is R = -acc_src:
+                        // segment 0 -> V = +acc_src = ~R + 1 (mask ~0), segment 1 -> V = -acc_src = R (mask 0).
+                        const uint32_t qr = (q0 + 256u * (uint32_t)(c >> 1)) & 4095u;
+                        const uint32_t qi = (qr + 1024u) & 4095u;
+                        pr = lanebase + (qr & 2047u); pi = lanebase + (qi & 2047u);
+                        tr = (qr >> 11) - 1u; ti = (qi >> 11) - 1u;
+                    }
+#pragma unroll
+                    for (int mm = 0; mm < 4; mm++) {
+                        const int m = c * 4 + mm;
+                        const int s = m & 7;
+                        const uint64_t r0 = pr[32 * s], r1 = pi[32 * s];
+                        const uint64_t e0 = pack64(h[4 * mm], h[4 * mm + 1]) + (r0 ^ pack64(tr, tr)) + pack64(tr & 1u, 0x7FFFFF00u);
+                        const uint64_t e1 = pack64(h[4 * mm + 2], h[4 * mm + 3]) + (r1 ^ pack64(ti, ti)) + pack64(ti & 1u, 0x7FFFFF00u);
+                        const uint32_t d0 = (uint32_t)(e0 >> 41), d1 = (uint32_t)(e1 >> 41);
+                        // digit + (2^22 - 1) in [0, 2^23) -> double by exponent trick (exact)
+                        double fr = dbl(d0, 0x43300000u) - 4503599631564799.0;
+                        double fi = dbl(d1, 0x43300000u) - 4503599631564799.0;
+                        PBS_DUMP(0, d0); PBS_DUMP(1, d1);
+                        twist_m(fr, fi, m);
+                        xr[brev5(m)] = fr; xi[brev5(m)] = fi;
+                    }
+                }
+            }
+            __syncwarp();  // all rotation reads done before the buffer is reused for the transposition
+            PBS5_TS(1);
+
+            // forward transform (fft.cuh: fwd1024), with the hand-over points of the pair protocol
+            {
+                uint32_t t0[16], t1[16];
+                fft32_dit<false>(xr, xi);
+                tw.issue(0, t0);
+#pragma unroll
+                for (int c2 = 0; c2 < 4; c2++) {
+                    tw.wait();
+                    tw.issue(2 * c2 + 1, t1);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const int k1 = 8 * c2 + kk;
+                        double2 y;
+                        cmul_tw<false>(y.x, y.y, xr[k1], xi[k1], t0, kk);
+                        tb_own[lane * kTStride + k1] = y;
+                    }
+                    tw.wait();
+                    if (c2 < 3) tw.issue(2 * c2 + 2, t0);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const int k1 = 8 * c2 + 4 + kk;
+                        double2 y;
+                        cmul_tw<false>(y.x, y.y, xr[k1], xi[k1], t1, kk);
+                        tb_own[lane * kTStride + k1] = y;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int l = 0; l < 32; l++) {
+                    const double2 v = tb_own[l * kTStride + lane];
+                    xr[brev5(l)] = v.x; xi[brev5(l)] = v.y;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_free);   // this warp's buffer may now receive the sibling's transform
+                fft32_dit_stages<false, 0, (PBS5_FUSE & 1) ? 3 : 4>(xr, xi);
+            }
+            PBS5_TS(2);
+
+            // hand the transform to the sibling (written into ITS buffer, layout [q][lane]); Out_p = B[p][p] F_p +
+            // B[1-p][p] F_{1-p} (update_with_fmadd, ggsw.rs:616-697), written into the bit-reversed slot the inverse
+            // transform wants.  The own product needs nothing from the sibling and hides the hand-over.
+            mbar_wait(bar_free, par);
+            mbar_wait(bsk_bar, par);
+            PBS5_TS(3);
+            PBS5_TS(4);
+            double zr[32], zi[32];
+            {
+                const double2 *b_own = bsk_s + (size_t)(p * 2 + p) * kHalf + lane;         // row p, column p
+                own_products<0, (PBS5_FUSE & 1) != 0>(zr, zi, xr, xi, b_own, tb_sib + lane);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full);
+            PBS5_TS(5);
+            mbar_wait(bar_full, par);
+            PBS5_TS(6);
+            {
+                const double2 *b_oth = bsk_s + (size_t)((1 - p) * 2 + p) * kHalf + lane;   // row 1-p, column p
+                const SiblingProduct oth{b_oth, tb_own + lane};
+                if (PBS5_FUSE & 2) {
+                    fft32_dit_df<true, 0, 32>(zr, zi, oth);   // inverse first pass (registers only), products at the leaves
+                } else {
+                    sibling_products<0>(zr, zi, oth);
+                    inv1024_pass1(zr, zi);
+                }
+            }
+            PBS5_TS(7);
+            // this warp is done with the slice (and with the sibling's transform); the last of the CTA's warps refills the slice buffer
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned int old = atomicAdd(consumed, 1u);
+                if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
+                    issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
+            }
+            PBS5_TS(8);
+            inv1024_rest(zr, zi, tb_own, tw, lane);
+            __syncwarp();  // transposition reads done before the rotation copy overwrites the buffer
+            PBS5_TS(9);
+
+            // phase D: untwist, from_torus, wrapping add (fft/mod.rs:285-304): acc += delta <=> G -= delta; refresh
+            // TMEM, the rotation copy and its overflow zone (negated first 256 coefficients)
+            {
+                uint32_t h0[16], h1[16];
+                tmem_ld16_nc(t_acc, h0);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t(&h)[16] = (c & 1) ? h1 : h0;
+                    tmem_wait_ld16(h);
+                    if (c < 7) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
+#pragma unroll
+                    for (int mm = 0; mm < 4; mm++) {
+                        const int m = c * 4 + mm;
+                        const int j = lane + 32 * m;
+                        double yr = zr[m], yi = zi[m];
+                        untwist_m(yr, yi, m);
+                        const uint64_t g0 = pack64(h[4 * mm], h[4 * mm + 1]) + kFtBias - from_torus_fp(yr);
+                        const uint64_t g1 = pack64(h[4 * mm + 2], h[4 * mm + 3]) + kFtBias - from_torus_fp(yi);
+                        PBS_DUMP(2, __double_as_longlong(yr)); PBS_DUMP(3, __double_as_longlong(yi));
+                        PBS_DUMP(4, from_torus_fp(yr) - kFtBias); PBS_DUMP(5, from_torus_fp(yi) - kFtBias);
+                        rot[j] = g0; rot[j + kHalf] = g1;
+                        if (c < 2) rot[kN + j] = 0 - g0;
+                        h[4 * mm] = (uint32_t)g0; h[4 * mm + 1] = (uint32_t)(g0 >> 32);
+                        h[4 * mm + 2] = (uint32_t)g1; h[4 * mm + 3] = (uint32_t)(g1 >> 32);
+                    }
+                    tmem_st16_nc(t_acc + c * 16, h);
+                }
+                tmem_wait_st();
+            }
+            __syncwarp();  // rotation copy complete before the next step's gather
+            PBS5_TS(10);
+        }
+
+        // ---------------------------------------------------------------- sample extraction (acc = -G)
+        uint64_t *o = a.out + (size_t)ct * (kN + 1);
+        if (p == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                uint32_t h[16];
+                tmem_ld16(t_acc + c * 16, h);
+                tmem_wait_ld();
+#pragma unroll
+                for (int mm = 0; mm < 4; mm++) {
+                    const int j = lane + 32 * (c * 4 + mm);
+                    const uint64_t g0 = pack64(h[4 * mm], h[4 * mm + 1]);       // = -acc[j]
+                    const uint64_t g1 = pack64(h[4 * mm + 2], h[4 * mm + 3]);   // = -acc[j + 1024]
+                    if (j == 0) o[0] = 0 - g0; else o[kN - j] = g0;
+                    o[kHalf - j] = g1;  // coefficient j + 1024 -> index N - (j + 1024), negated
+                }
+            }
+        } else {
+            uint32_t h[16];
+            tmem_ld16(t_acc, h);
+            tmem_wait_ld();
+            if (lane == 0) o[kN] = 0 - pack64(h[0], h[1]);
+        }
+    }
+
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, kTmemCols);
+}
+
+}  // namespace b200
