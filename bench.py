@@ -400,9 +400,9 @@ def run_b200(args):
         achieved = B * FLOP_PER_PBS / (pbs_ms * 1e-3) / 1e12
         n_waves = -(-B // (148 * 4))
         traffic, traffic_src = None, None
-        for prof in ("r02_final_ncu_metrics.json", "r01_final_ncu_metrics.json"):
+        for prof in ("r02b_final_ncu_metrics.json",):
             try:   # DRAM bytes of the dominant kernel from the committed ncu --set full capture (same batch only)
-                m = json.load(open(os.path.join(ROOT, "profiles", prof)))["pbs_kernel3<4>"]
+                m = json.load(open(os.path.join(ROOT, "profiles", prof)))["pbs_kernel5<4>"]
                 if m["batch"] == B:
                     traffic, traffic_src = m["dram_bytes_read"] + m["dram_bytes_write"], prof
                     break
@@ -428,7 +428,7 @@ def run_b200(args):
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/{traffic_src}",
-                "kernel": "pbs_kernel3", "kernel_ms": pbs_ms, "ks_kernel_ms": ks_ms,
+                "kernel": "pbs_kernel5", "kernel_ms": pbs_ms, "ks_kernel_ms": ks_ms,
                 "ks_int8_TOPs": B * KS_MACS * 2 / (ks_ms * 1e-3) / 1e12,
                 "kernel_share_of_step": pbs_ms / ms_per_step, "peak_source": peak_src,
                 "algorithmic_flop_per_unit": FLOP_PER_PBS,

@@ -54,6 +54,13 @@ __device__ __forceinline__ uint64_t from_torus_fp(const double x) {
 #ifndef PBS5_FUSE
 #define PBS5_FUSE 0
 #endif
+// bit 2 = the accumulator's TMEM chunks hold the slots in the bit-reversed order in which the forward transform's first
+// pass consumes its registers (chunk c, element k <-> slot brev5(4c + k)), so that butterflies become ready while the
+// gather is still running.
+#ifndef PBS5_ORDER
+#define PBS5_ORDER 0
+#endif
+__host__ __device__ constexpr int slot5(const int c, const int k) { return PBS5_ORDER ? brev5(4 * c + k) : 4 * c + k; }
 
 // stages [kFirst, kLast] (butterfly distance 2^stage) of the in-register 32-point DIT transform of fft.cuh
 template <bool INV, int kFirst, int kLast>
@@ -132,7 +139,17 @@ __device__ __forceinline__ void own_products(double (&zr)[32], double (&zi)[32],
 #define PBS5_TS(k) do { } while (0)
 #endif
 
-template <int kCts>
+#ifdef B200TFHE_LAB_DELAY
+__device__ int g_lab_delay;   // development (tools/lab): warps 4-7 enter the CMUX loop this many cycles late
+#endif
+
+// kPhase = 1 (4 full ciphertexts per CTA only): the two halves of the CTA run HALF A STEP apart.  Warps 0-3 ("early") and
+// warps 4-7 ("late") share their SM sub-partitions pairwise; a step is cut at the hand-over of the transforms into
+// [gather, forward transform, own product] and [sibling product, inverse transform, from_torus], about 7k cycles each for
+// a warp running alone, and the late half starts its first part when the early half starts its second (named barriers 5
+// and 6, bar.arrive / bar.sync over 256 threads).  The two warps of a sub-partition then want different units most of
+// the time (FP64 pipe vs issue slots / shared memory) instead of the same unit at the same time.
+template <int kCts, int kPhase = 0>
 __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,6 +198,8 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
     }
     const int n_act_cts = min(kCts, a.batch - (int)blockIdx.x * kCts);
     const unsigned int n_act_warps = 2u * (unsigned int)n_act_cts;
+    const bool dephase = kPhase > 0 && kCts == 4 && n_act_cts == 4;   // CTA-uniform
+    const bool late = warp >= 4;
     if (threadIdx.x == 0) issue_bsk_slice(bsk_s, a.bsk, 0, bsk_bar);
     tmem_fence_before();
     __syncthreads();
@@ -198,14 +217,15 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
             uint32_t h[16];
 #pragma unroll
             for (int mm = 0; mm < 4; mm++) {
-                const int j = lane + 32 * (c * 4 + mm);
+                const int m = slot5(c, mm);
+                const int j = lane + 32 * m;
                 const uint32_t i0 = (uint32_t)(j + bhat) & 4095u, i1 = (i0 + 1024u) & 4095u;
                 uint64_t v0 = lut[i0 & 2047u], v1 = lut[i1 & 2047u];
                 if (i0 & 2048u) v0 = 0 - v0;
                 if (i1 & 2048u) v1 = 0 - v1;
                 const uint64_t g0 = 0 - v0, g1 = 0 - v1;
                 rot[j] = g0; rot[j + kHalf] = g1;
-                if (c < 2) rot[kN + j] = v0;
+                if (m < 8) rot[kN + j] = v0;
                 h[4 * mm] = (uint32_t)g0; h[4 * mm + 1] = (uint32_t)(g0 >> 32);
                 h[4 * mm + 2] = (uint32_t)g1; h[4 * mm + 3] = (uint32_t)(g1 >> 32);
             }
@@ -214,19 +234,35 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
         tmem_wait_st();
         ct_barrier(1 + ctl);  // a~ table visible to both warps; rotation copy visible within the warp
 
+#ifdef B200TFHE_LAB_DELAY
+        if (warp >= 4) { const long long t_in = clock64(); while (clock64() - t_in < g_lab_delay) { } }
+#endif
         // ---------------------------------------------------------------- CMUX loop
         // Steps with a~ = 0 (mod 2N) are not skipped as the reference does (bootstrap.rs:281): the rotation is then the
         // identity, every digit is 0 and the step adds exactly zero.
         for (int i = 0; i < a.n; i++) {
             const uint32_t par = (uint32_t)(i & 1);
+            if (dephase) {
+                if (late) bar_sync_n(5, 256);           // the early half has reached the middle of step i
+                else if (i > 0) bar_sync_n(6, 256);     // the late half has reached the middle of step i - 1
+            }
             PBS5_TS(0);
             double xr[32], xi[32];
             // phase A: ct1 = acc * X^a~ - acc, round + digit (ggsw.rs:514-521), exact int -> double, twist by C_m
             {
                 const uint32_t q0 = (4096u - (uint32_t)ahat[i]) & 4095u;   // source index (in the 4096-periodic extension) of coefficient 0
                 const uint64_t *lanebase = rot + lane;
-                const uint64_t *pr = lanebase, *pi = lanebase;
-                uint32_t tr = 0, ti = 0;
+                // group g = slots 8g .. 8g+7 (g < 4: coefficients < 1024, g >= 4: the second half): one segment / offset for
+                // all lanes and all 8 slots.  Stored word is R = -acc_src: segment 0 -> V = +acc_src = ~R + 1 (mask ~0),
+                // segment 1 -> V = -acc_src = R (mask 0).
+                const uint64_t *gp[8];
+                uint32_t gt[8];
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    const uint32_t qg = (q0 + 256u * (uint32_t)g) & 4095u;
+                    gp[g] = lanebase + (qg & 2047u);
+                    gt[g] = (qg >> 11) - 1u;
+                }
                 uint32_t h0[16], h1[16];
                 tmem_ld16_nc(t_acc, h0);
 #pragma unroll
@@ -234,20 +270,12 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                     uint32_t(&h)[16] = (c & 1) ? h1 : h0;
                     tmem_wait_ld16(h);
                     if (c < 7) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
-                    if ((c & 1) == 0) {
-                        // group (c >> 1) of the first half and of the second half (1024 coefficients further on): one
-                        // segment / offset for all lanes and all 8 slots of the group.  Stored word is R = -acc_src:
-                        // segment 0 -> V = +acc_src = ~R + 1 (mask ~0), segment 1 -> V = -acc_src = R (mask 0).
-                        const uint32_t qr = (q0 + 256u * (uint32_t)(c >> 1)) & 4095u;
-                        const uint32_t qi = (qr + 1024u) & 4095u;
-                        pr = lanebase + (qr & 2047u); pi = lanebase + (qi & 2047u);
-                        tr = (qr >> 11) - 1u; ti = (qi >> 11) - 1u;
-                    }
 #pragma unroll
                     for (int mm = 0; mm < 4; mm++) {
-                        const int m = c * 4 + mm;
-                        const int s = m & 7;
-                        const uint64_t r0 = pr[32 * s], r1 = pi[32 * s];
+                        const int m = slot5(c, mm);
+                        const int g = m >> 3, sl = m & 7;
+                        const uint32_t tr = gt[g], ti = gt[4 + g];
+                        const uint64_t r0 = gp[g][32 * sl], r1 = gp[4 + g][32 * sl];
                         const uint64_t e0 = pack64(h[4 * mm], h[4 * mm + 1]) + (r0 ^ pack64(tr, tr)) + pack64(tr & 1u, 0x7FFFFF00u);
                         const uint64_t e1 = pack64(h[4 * mm + 2], h[4 * mm + 3]) + (r1 ^ pack64(ti, ti)) + pack64(ti & 1u, 0x7FFFFF00u);
                         const uint32_t d0 = (uint32_t)(e0 >> 41), d1 = (uint32_t)(e1 >> 41);
@@ -260,13 +288,13 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                     }
                 }
             }
-            __syncwarp();  // all rotation reads done before the buffer is reused for the transposition
             PBS5_TS(1);
 
             // forward transform (fft.cuh: fwd1024), with the hand-over points of the pair protocol
             {
                 uint32_t t0[16], t1[16];
                 fft32_dit<false>(xr, xi);
+                __syncwarp();  // all rotation reads done before the buffer is reused for the transposition
                 tw.issue(0, t0);
 #pragma unroll
                 for (int c2 = 0; c2 < 4; c2++) {
@@ -315,6 +343,10 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full);
+            if (dephase) {
+                if (!late) bar_arrive(5, 256);
+                else if (i + 1 < a.n) bar_arrive(6, 256);
+            }
             PBS5_TS(5);
             mbar_wait(bar_full, par);
             PBS5_TS(6);
@@ -337,8 +369,7 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                     issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
             }
             PBS5_TS(8);
-            inv1024_rest(zr, zi, tb_own, tw, lane);
-            __syncwarp();  // transposition reads done before the rotation copy overwrites the buffer
+            inv1024_rest(zr, zi, tb_own, tw, lane);   // (its transposition reads are complete before its second pass starts)
             PBS5_TS(9);
 
             // phase D: untwist, from_torus, wrapping add (fft/mod.rs:285-304): acc += delta <=> G -= delta; refresh
@@ -353,7 +384,7 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                     if (c < 7) tmem_ld16_nc(t_acc + (c + 1) * 16, (c & 1) ? h0 : h1);
 #pragma unroll
                     for (int mm = 0; mm < 4; mm++) {
-                        const int m = c * 4 + mm;
+                        const int m = slot5(c, mm);
                         const int j = lane + 32 * m;
                         double yr = zr[m], yi = zi[m];
                         untwist_m(yr, yi, m);
@@ -362,7 +393,7 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                         PBS_DUMP(2, __double_as_longlong(yr)); PBS_DUMP(3, __double_as_longlong(yi));
                         PBS_DUMP(4, from_torus_fp(yr) - kFtBias); PBS_DUMP(5, from_torus_fp(yi) - kFtBias);
                         rot[j] = g0; rot[j + kHalf] = g1;
-                        if (c < 2) rot[kN + j] = 0 - g0;
+                        if (m < 8) rot[kN + j] = 0 - g0;
                         h[4 * mm] = (uint32_t)g0; h[4 * mm + 1] = (uint32_t)(g0 >> 32);
                         h[4 * mm + 2] = (uint32_t)g1; h[4 * mm + 3] = (uint32_t)(g1 >> 32);
                     }
@@ -384,7 +415,7 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                 tmem_wait_ld();
 #pragma unroll
                 for (int mm = 0; mm < 4; mm++) {
-                    const int j = lane + 32 * (c * 4 + mm);
+                    const int j = lane + 32 * slot5(c, mm);
                     const uint64_t g0 = pack64(h[4 * mm], h[4 * mm + 1]);       // = -acc[j]
                     const uint64_t g1 = pack64(h[4 * mm + 2], h[4 * mm + 3]);   // = -acc[j + 1024]
                     if (j == 0) o[0] = 0 - g0; else o[kN - j] = g0;

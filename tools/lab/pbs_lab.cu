@@ -35,11 +35,11 @@ static void launch3(const PbsArgs &a, cudaStream_t s) {
     pbs_kernel3<CTS, PH><<<(a.batch + CTS - 1) / CTS, CTS * 64, smem, s>>>(a);
 }
 
-template <int CTS>
+template <int CTS, int PH = 0>
 static void launch5(const PbsArgs &a, cudaStream_t s) {
     constexpr size_t smem = pbs5_smem_bytes<CTS>();
-    CK(cudaFuncSetAttribute(pbs_kernel5<CTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pbs_kernel5<CTS><<<(a.batch + CTS - 1) / CTS, CTS * 64, smem, s>>>(a);
+    CK(cudaFuncSetAttribute(pbs_kernel5<CTS, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pbs_kernel5<CTS, PH><<<(a.batch + CTS - 1) / CTS, CTS * 64, smem, s>>>(a);
 }
 
 int main(int argc, char **argv) {
@@ -63,12 +63,16 @@ int main(int argc, char **argv) {
     CK(cudaMalloc(&d_lwe, lwe.size() * 8)); CK(cudaMemcpy(d_lwe, lwe.data(), lwe.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_lut, lut.size() * 8)); CK(cudaMemcpy(d_lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_out, (size_t)batch * (kN + 1) * 8)); CK(cudaMalloc(&d_out2, (size_t)batch * (kN + 1) * 8));
+#ifdef B200TFHE_LAB_DELAY
+    { const int dl = getenv("LAB_DELAY") ? atoi(getenv("LAB_DELAY")) : 0; CK(cudaMemcpyToSymbol(g_lab_delay, &dl, sizeof(int))); }
+#endif
     PbsArgs a{};
     a.lwe_small = d_lwe; a.lut_idx = nullptr; a.luts = d_lut; a.bsk = d_bsk; a.twid = d_tw; a.out = d_out; a.batch = batch; a.n = n; a.n_luts = 1; a.err_flag = nullptr; a.dbg = nullptr;
     const size_t ndbg = 8 * 8 * 16;
     if (tl) { CK(cudaMalloc(&a.dbg, ndbg * sizeof(long long))); CK(cudaMemset(a.dbg, 0, ndbg * sizeof(long long))); }
     auto run = [&](const PbsArgs &x) {
         if (kernel == 31) launch3<4, 1>(x, 0);
+        else if (kernel == 51) launch5<4, 1>(x, 0);
         else if (kernel == 5) {
             switch (cts) { case 1: launch5<1>(x, 0); break; case 2: launch5<2>(x, 0); break; case 3: launch5<3>(x, 0); break; default: launch5<4>(x, 0); }
         }
