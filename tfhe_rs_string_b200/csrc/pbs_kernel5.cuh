@@ -48,6 +48,23 @@ __device__ __forceinline__ uint64_t from_torus_fp(const double x) {
     const double u = fma(l, 18446744073709551616.0, 6755399441055744.0);
     return pack64((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u) + ((uint32_t)__double2loint(t) << 18));
 }
+// G -= from_torus(x) on the two 32-bit halves of G, in three integer instructions (subtract with borrow; the bias of u
+// and the 14 top bits from t go into the high word with one multiply-add), and the rotation copy written straight from
+// the register pair the TMEM store uses.
+__device__ __forceinline__ void acc_sub_from_torus(uint32_t &glo, uint32_t &ghi, const double x) {
+    // the magic constant is lowered by 0x10CE ulps (0x10CE << 18 = 0x43380000, the high word of 1.5 * 2^52), so that the
+    // multiply-add below removes the bias of u together with placing t's 14 bits: -(t.lo - 0x10CE) << 18
+    const double m1 = __longlong_as_double(0x4257FFFFFFFFEF32ll);   // 1.5 * 2^38 - 0x10CE * 2^-14
+    const double t = x + m1;
+    const double l = x - (t - m1);
+    const double u = fma(l, 18446744073709551616.0, 6755399441055744.0);
+    uint32_t hi;
+    asm("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %3, %4;" : "+r"(glo), "=r"(hi) : "r"((uint32_t)__double2loint(u)), "r"(ghi), "r"((uint32_t)__double2hiint(u)));
+    ghi = (uint32_t)__double2loint(t) * 0xFFFC0000u + hi;
+}
+__device__ __forceinline__ void sts_v2(uint64_t *p, const uint32_t lo, const uint32_t hi) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(lo), "r"(hi) : "memory");
+}
 
 // Development switches (tools/lab): bit 0 = last stage of the forward transform fused with the hand-over and the own
 // product; bit 1 = sibling product at the leaves of a depth-first inverse first pass.
@@ -388,14 +405,13 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                         const int j = lane + 32 * m;
                         double yr = zr[m], yi = zi[m];
                         untwist_m(yr, yi, m);
-                        const uint64_t g0 = pack64(h[4 * mm], h[4 * mm + 1]) + kFtBias - from_torus_fp(yr);
-                        const uint64_t g1 = pack64(h[4 * mm + 2], h[4 * mm + 3]) + kFtBias - from_torus_fp(yi);
                         PBS_DUMP(2, __double_as_longlong(yr)); PBS_DUMP(3, __double_as_longlong(yi));
                         PBS_DUMP(4, from_torus_fp(yr) - kFtBias); PBS_DUMP(5, from_torus_fp(yi) - kFtBias);
-                        rot[j] = g0; rot[j + kHalf] = g1;
-                        if (m < 8) rot[kN + j] = 0 - g0;
-                        h[4 * mm] = (uint32_t)g0; h[4 * mm + 1] = (uint32_t)(g0 >> 32);
-                        h[4 * mm + 2] = (uint32_t)g1; h[4 * mm + 3] = (uint32_t)(g1 >> 32);
+                        acc_sub_from_torus(h[4 * mm], h[4 * mm + 1], yr);
+                        acc_sub_from_torus(h[4 * mm + 2], h[4 * mm + 3], yi);
+                        sts_v2(rot + j, h[4 * mm], h[4 * mm + 1]);
+                        sts_v2(rot + j + kHalf, h[4 * mm + 2], h[4 * mm + 3]);
+                        if (m < 8) rot[kN + j] = 0 - pack64(h[4 * mm], h[4 * mm + 1]);
                     }
                     tmem_st16_nc(t_acc + c * 16, h);
                 }

@@ -18,7 +18,7 @@
 // Mapping: 8 warps per CTA, quadrant q = warp & 3 hosts one polynomial: ciphertext q >> 1, polynomial
 // q & 1, half h = warp >> 2; 1 or 2 ciphertexts per CTA (quadrants 2, 3 idle for 1).
 #pragma once
-#include "pbs_kernel3.cuh"
+#include "pbs_kernel5.cuh"
 
 namespace b200 {
 
@@ -165,9 +165,12 @@ __device__ __forceinline__ void lat_inv_pass(double (&xr)[16], double (&xi)[16],
     }
 }
 
+// per ciphertext: two polynomial buffers (rotation copy with its overflow zone / transposition / transform, see
+// pbs_kernel5.cuh) and the a~ table
+__host__ __device__ constexpr size_t pbs_lat_ct_bytes() { return (size_t)2 * kBuf5Bytes + kMaxSmallDim * sizeof(uint16_t); }
 template <int CTS>
 __host__ __device__ constexpr size_t pbs_lat_smem_bytes() {
-    return kPbsHeaderBytes + kBskSliceBytes + (size_t)CTS * pbs_ct_smem_bytes();
+    return kPbsHeaderBytes + kBskSliceBytes + (size_t)CTS * pbs_lat_ct_bytes();
 }
 
 // CTS = 1, 2: 8 warps (latency); CTS = 4: 16 warps, 128 registers per thread, two polynomial pairs per
@@ -188,11 +191,11 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
     uint64_t *bsk_bar = reinterpret_cast<uint64_t *>(smem + 8);
     unsigned int *consumed = reinterpret_cast<unsigned int *>(smem + 16);
     double2 *bsk_s = reinterpret_cast<double2 *>(smem + kPbsHeaderBytes);
-    unsigned char *ctbase = smem + kPbsHeaderBytes + kBskSliceBytes + (size_t)(ctl < CTS ? ctl : 0) * pbs_ct_smem_bytes();
-    double2 *tb_own = reinterpret_cast<double2 *>(ctbase) + p * kTBufElems;            // shared by the two warps of the polynomial
-    const double2 *tb_oth = reinterpret_cast<double2 *>(ctbase) + (1 - p) * kTBufElems;
-    uint16_t *ahat = reinterpret_cast<uint16_t *>(ctbase + (size_t)2 * kTBufElems * sizeof(double2));
-    uint64_t *rot = reinterpret_cast<uint64_t *>(tb_own);   // rotation copy (r = -acc) aliases the transposition buffer
+    unsigned char *ctbase = smem + kPbsHeaderBytes + kBskSliceBytes + (size_t)(ctl < CTS ? ctl : 0) * pbs_lat_ct_bytes();
+    double2 *tb_own = reinterpret_cast<double2 *>(ctbase + (size_t)p * kBuf5Bytes);            // shared by the two warps of the polynomial
+    const double2 *tb_oth = reinterpret_cast<const double2 *>(ctbase + (size_t)(1 - p) * kBuf5Bytes);
+    uint16_t *ahat = reinterpret_cast<uint16_t *>(ctbase + (size_t)2 * kBuf5Bytes);
+    uint64_t *rot = reinterpret_cast<uint64_t *>(tb_own);   // rotation copy (G = -acc, + overflow zone, pbs_kernel5.cuh) aliases the transposition buffer
 
     if (warp == 0) tmem_alloc(slot, 512);
     if (threadIdx.x == 0) {
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
         for (int i = (p * 2 + h) * 32 + lane; i < a.n; i += 128) ahat[i] = (uint16_t)modswitch2048(lwe[i]);
         const uint32_t bhat = modswitch2048(lwe[a.n]);
         const uint64_t *lut = a.luts + ((size_t)pbs_lut_id(a, ct) * 2 + p) * kN;
-        // acc = LUT * X^-b~ (polynomial_algorithms.rs:315-354); TMEM holds G = C - acc, shared memory r = -acc
+        // acc = LUT * X^-b~ (polynomial_algorithms.rs:315-354); TMEM and the rotation copy hold G = -acc
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             uint32_t hh[16];
@@ -247,8 +250,9 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
                 uint64_t v0 = lut[i0 & 2047u], v1 = lut[i1 & 2047u];
                 if (i0 & 2048u) v0 = 0 - v0;
                 if (i1 & 2048u) v1 = 0 - v1;
-                rot[j] = 0 - v0; rot[j + kHalf] = 0 - v1;
-                const uint64_t g0 = kAccC - v0, g1 = kAccC - v1;
+                const uint64_t g0 = 0 - v0, g1 = 0 - v1;
+                rot[j] = g0; rot[j + kHalf] = g1;
+                if (j < kZone5) rot[kN + j] = v0;
                 hh[4 * k] = (uint32_t)g0; hh[4 * k + 1] = (uint32_t)(g0 >> 32);
                 hh[4 * k + 2] = (uint32_t)g1; hh[4 * k + 3] = (uint32_t)(g1 >> 32);
             }
@@ -263,13 +267,17 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
             double xr[16], xi[16];
             // phase A: ct1 = acc * X^a~ - acc, round + digit, exact int -> double, twist by C_m (see pbs_kernel3.cuh)
             {
-                const uint32_t ah = ahat[i];
-                const uint32_t base0 = (uint32_t)(lane + 512 * h + 4096 - (int)ah) & 4095u;   // source index of coefficient lane + 32*16h
-                const uint32_t base1 = (base0 + 1024u) & 4095u;
-                const uint32_t pos0 = base0 & 2047u, pos1 = base1 & 2047u;
-                const uint32_t tn0 = (base0 & 2048u) ? 0u : 0xFFFFFFFFu, tn1 = (base1 & 2048u) ? 0u : 0xFFFFFFFFu;
-                const int mc0 = (int)((2048u - pos0 + 31u) >> 5), mc1 = (int)((2048u - pos1 + 31u) >> 5);
-                const uint64_t *pn0 = rot + pos0, *pn1 = rot + pos1;
+                // group-uniform gather of pbs_kernel5.cuh: this thread's slots 16 h .. 16 h + 15 of either half are two groups of 8
+                const uint32_t q0 = (4096u - (uint32_t)ahat[i]) & 4095u;
+                const uint64_t *lanebase = rot + lane;
+                const uint64_t *gp[4];
+                uint32_t gt[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {   // groups 2h, 2h + 1 (first half) and 4 + 2h, 5 + 2h (second half)
+                    const uint32_t qg = (q0 + 256u * (uint32_t)(2 * h + (g & 1) + 4 * (g >> 1))) & 4095u;
+                    gp[g] = lanebase + (qg & 2047u);
+                    gt[g] = (qg >> 11) - 1u;
+                }
                 uint32_t h0[16], h1[16];
                 tmem_ld16_nc(t_acc, h0);
 #pragma unroll
@@ -280,12 +288,11 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const int mm = 4 * c + k;
-                        const bool w0 = mm >= mc0, w1 = mm >= mc1;
-                        const uint64_t r0 = (w0 ? pn0 - kN : pn0)[32 * mm], r1 = (w1 ? pn1 - kN : pn1)[32 * mm];
-                        const uint32_t t0 = w0 ? ~tn0 : tn0, t1 = w1 ? ~tn1 : tn1;
-                        const uint64_t T0 = pack64(t0, t0), T1 = pack64(t1, t1);
-                        const uint64_t e0 = pack64(hh[4 * k], hh[4 * k + 1]) + (r0 ^ T0) - T0;
-                        const uint64_t e1 = pack64(hh[4 * k + 2], hh[4 * k + 3]) + (r1 ^ T1) - T1;
+                        const int g = mm >> 3, sl = mm & 7;
+                        const uint32_t tr = gt[g], ti = gt[2 + g];
+                        const uint64_t r0 = gp[g][32 * sl], r1 = gp[2 + g][32 * sl];
+                        const uint64_t e0 = pack64(hh[4 * k], hh[4 * k + 1]) + (r0 ^ pack64(tr, tr)) + pack64(tr & 1u, 0x7FFFFF00u);
+                        const uint64_t e1 = pack64(hh[4 * k + 2], hh[4 * k + 3]) + (r1 ^ pack64(ti, ti)) + pack64(ti & 1u, 0x7FFFFF00u);
                         const double fr = dbl((uint32_t)(e0 >> 41), 0x43300000u) - 4503599631564799.0;
                         const double fi = dbl((uint32_t)(e1 >> 41), 0x43300000u) - 4503599631564799.0;
                         const double2 cm = c_twm[16 * h + mm];
@@ -389,14 +396,6 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
 
             PBS3_TS(8);
             // ---- phase D: untwist, from_torus, G -= delta, refresh both copies
-            uint64_t dl0[16], dl1[16];
-#pragma unroll
-            for (int mm = 0; mm < 16; mm++) {
-                const double2 cm = c_twm[16 * h + mm];
-                const double ur = fma(yi[mm], cm.y, yr[mm] * cm.x);
-                const double ui = fma(yi[mm], cm.x, -(yr[mm] * cm.y));
-                dl0[mm] = from_torus_exp(ur); dl1[mm] = from_torus_exp(ui);
-            }
             {
                 uint32_t h0[16], h1[16];
                 tmem_ld16_nc(t_acc, h0);
@@ -409,9 +408,14 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
                     for (int k = 0; k < 4; k++) {
                         const int mm = 4 * c + k;
                         const int j = lane + 32 * (mm + 16 * h);
-                        const uint64_t g0 = pack64(hh[4 * k], hh[4 * k + 1]) - dl0[mm];
-                        const uint64_t g1 = pack64(hh[4 * k + 2], hh[4 * k + 3]) - dl1[mm];
-                        rot[j] = g0 - kAccC; rot[j + kHalf] = g1 - kAccC;
+                        const double2 cm = c_twm[16 * h + mm];
+                        const double ur = fma(yi[mm], cm.y, yr[mm] * cm.x);
+                        const double ui = fma(yi[mm], cm.x, -(yr[mm] * cm.y));
+                        // acc += delta <=> G -= delta (from_torus on the FP64 pipe, pbs_kernel5.cuh)
+                        const uint64_t g0 = pack64(hh[4 * k], hh[4 * k + 1]) + kFtBias - from_torus_fp(ur);
+                        const uint64_t g1 = pack64(hh[4 * k + 2], hh[4 * k + 3]) + kFtBias - from_torus_fp(ui);
+                        rot[j] = g0; rot[j + kHalf] = g1;
+                        if (j < kZone5) rot[kN + j] = 0 - g0;   // (warp-uniform: h == 0, mm < 8)
                         hh[4 * k] = (uint32_t)g0; hh[4 * k + 1] = (uint32_t)(g0 >> 32);
                         hh[4 * k + 2] = (uint32_t)g1; hh[4 * k + 3] = (uint32_t)(g1 >> 32);
                     }
@@ -435,17 +439,17 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int j = lane + 32 * (16 * h + 4 * c + k);
-                    const uint64_t a0 = kAccC - pack64(hh[4 * k], hh[4 * k + 1]);
-                    const uint64_t a1 = kAccC - pack64(hh[4 * k + 2], hh[4 * k + 3]);
-                    if (j == 0) o[0] = a0; else o[kN - j] = 0 - a0;
-                    o[kHalf - j] = 0 - a1;
+                    const uint64_t g0 = pack64(hh[4 * k], hh[4 * k + 1]);       // = -acc[j]
+                    const uint64_t g1 = pack64(hh[4 * k + 2], hh[4 * k + 3]);   // = -acc[j + 1024]
+                    if (j == 0) o[0] = 0 - g0; else o[kN - j] = g0;
+                    o[kHalf - j] = g1;
                 }
             }
         } else if (h == 0) {
             uint32_t hh[16];
             tmem_ld16(t_acc, hh);
             tmem_wait_ld();
-            if (lane == 0) o[kN] = kAccC - pack64(hh[0], hh[1]);
+            if (lane == 0) o[kN] = 0 - pack64(hh[0], hh[1]);
         }
     }
 

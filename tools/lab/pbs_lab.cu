@@ -9,6 +9,7 @@
 #include <random>
 #include "../../tfhe_rs_string_b200/csrc/pbs_kernel3.cuh"
 #include "../../tfhe_rs_string_b200/csrc/pbs_kernel5.cuh"
+#include "../../tfhe_rs_string_b200/csrc/pbs_kernel_lat.cuh"
 #ifdef LAB_HAVE_K4
 #include "../../tfhe_rs_string_b200/csrc/pbs_kernel4.cuh"
 #endif
@@ -42,6 +43,13 @@ static void launch5(const PbsArgs &a, cudaStream_t s) {
     pbs_kernel5<CTS, PH><<<(a.batch + CTS - 1) / CTS, CTS * 64, smem, s>>>(a);
 }
 
+template <int CTS>
+static void launch_lat(const PbsArgs &a, cudaStream_t s) {
+    constexpr size_t smem = pbs_lat_smem_bytes<CTS>();
+    CK(cudaFuncSetAttribute(pbs_lat_kernel<CTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pbs_lat_kernel<CTS><<<(a.batch + CTS - 1) / CTS, 256, smem, s>>>(a);
+}
+
 int main(int argc, char **argv) {
     const int kernel = argc > 1 ? atoi(argv[1]) : 3;
     const int cts = argc > 2 ? atoi(argv[2]) : 4;
@@ -73,6 +81,7 @@ int main(int argc, char **argv) {
     auto run = [&](const PbsArgs &x) {
         if (kernel == 31) launch3<4, 1>(x, 0);
         else if (kernel == 51) launch5<4, 1>(x, 0);
+        else if (kernel == 7) { if (cts == 1) launch_lat<1>(x, 0); else launch_lat<2>(x, 0); }
         else if (kernel == 5) {
             switch (cts) { case 1: launch5<1>(x, 0); break; case 2: launch5<2>(x, 0); break; case 3: launch5<3>(x, 0); break; default: launch5<4>(x, 0); }
         }
