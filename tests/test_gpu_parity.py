@@ -64,7 +64,7 @@ def test_keyswitch_adversarial_inputs(engine, real_keys):
 
 
 # batch -> kernel chosen by the launcher on a 148-SM part (b200tfhe.cu:launch_pbs_fast): 40 -> pbs_lat_kernel<1>,
-# 200 -> pbs_lat_kernel<2>, 400 -> pbs_kernel3<3>, 500 -> pbs_kernel3<4> (one wave), 1024 -> pbs_kernel3<4> (two waves,
+# 200 -> pbs_lat_kernel<2>, 400 -> pbs_kernel5<3>, 500 -> pbs_kernel5<4> (one wave), 1024 -> pbs_kernel5<4> (two waves,
 # BASELINE configs[0]): the throughput kernel that the benchmark times is compared with the oracle like the others.
 @pytest.mark.parametrize("batch", [40, 200, 400, 500, 1024])
 def test_pbs_parity(engine, real_keys, batch):

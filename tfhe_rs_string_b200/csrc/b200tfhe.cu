@@ -1,6 +1,6 @@
 // b200tfhe.cu -- C ABI of libb200tfhe.so (include/b200tfhe.h): context lifetime, key upload, LUT store, batched
 // keyswitch / bootstrap entry points on host and device buffers, multi-GPU sharding, level-synchronous programs.
-// Kernels: pbs_kernel3.cuh / pbs_kernel_lat.cuh (k = 1, N = 2048, l = 1), pbs_generic.cuh (every other classic
+// Kernels: pbs_kernel5.cuh / pbs_kernel_lat.cuh (k = 1, N = 2048, l = 1), pbs_generic.cuh (every other classic
 // parameter set), ks_mma.cuh (keyswitch on tcgen05), lwe_linear.cuh.  State and scheduler: context.hpp.
 #include "../../include/b200tfhe.h"
 
