@@ -136,7 +136,7 @@ struct DevCtx {
 
 struct b200tfhe_ctx {
     b200tfhe_params p{};
-    bool fast_path = false;                         // k = 1, N = 2048, one level of base 2^23: pbs_kernel3 / pbs_lat_kernel
+    bool fast_path = false;                         // k = 1, N = 2048, one level of base 2^23: pbs_kernel5 / pbs_lat_kernel
     bool ks_tensor = true;                          // keyswitch on tcgen05 (else ks_generic_kernel)
     int log2N = 11;
     bool fft_in_smem = true;

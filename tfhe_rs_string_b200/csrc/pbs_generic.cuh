@@ -1,6 +1,6 @@
 // pbs_generic.cuh -- programmable bootstrap for ANY classic parameter set (glwe_dimension k >= 1, polynomial
 // size N = 256 .. 32768, any decomposition base / level count), templated on the torus word (u64 shortint,
-// u32 boolean).  One CTA per ciphertext; the specialised kernels (pbs_kernel3.cuh, pbs_kernel_lat.cuh) take over
+// u32 boolean).  One CTA per ciphertext; the specialised kernels (pbs_kernel5.cuh, pbs_kernel_lat.cuh) take over
 // for k = 1, N = 2048, one level of base 2^23 -- this file is the coverage path for the other sets of
 // shortint/parameters/mod.rs (PARAM_MESSAGE_1_CARRY_1 k=3 N=512 :613-627, 3_3 N=8192 l=2 :853-867, 4_4 N=32768
 // :1063-1077) and boolean/parameters/mod.rs:123-192.

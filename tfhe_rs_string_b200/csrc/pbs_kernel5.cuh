@@ -1,8 +1,14 @@
-// pbs_kernel5.cuh -- fourth generation of the batched programmable bootstrap for k = 1, N = 2048, one level of
-// base 2^23 (same contract, data layouts and reference citations as pbs_kernel3.cuh; one warp per GLWE polynomial,
-// kCts ciphertexts per CTA, one CTA per SM).  What changed against pbs_kernel3 (measured there: every phase of a CMUX
-// step is bound by ONE unit that both warps of an SM sub-partition want at the same time -- gather: instruction
-// issue, transforms: FP64 pipe, exchange: shared memory + pair barriers, from_torus: the conversion unit):
+// pbs_kernel5.cuh -- the batched programmable bootstrap for k = 1, N = 2048, one level of base 2^23
+// (PARAM_MESSAGE_2_CARRY_2 and the other N = 2048 classic sets): one warp per GLWE polynomial, kCts ciphertexts per CTA,
+// one CTA per SM.  Replaces FourierLweBootstrapKeyView::bootstrap (core_crypto/fft_impl/fft64/crypto/bootstrap.rs:333-364):
+// mod-switch (fft_impl/common.rs:26-43), accumulator setup LUT * X^-b~ (polynomial_algorithms.rs:315-354), lwe_dimension
+// CMUX steps acc += GGSW_i (x) (acc * X^a~_i - acc) (bootstrap.rs:267-331, ggsw.rs:477-598: decompose, forward negacyclic
+// FFT, multiply-accumulate with the Fourier BSK, inverse FFT, from_torus, wrapping add), sample extraction
+// (lwe_sample_extraction, glwe_sample_extraction.rs).  Data layouts: DESIGN.md section 3.
+//
+// Against its predecessor pbs_kernel3 (tools/lab/pbs_kernel3.cuh, kept as the bit-for-bit regression reference; measured
+// there: every phase of a CMUX step is bound by ONE unit that both warps of an SM sub-partition want at the same time --
+// gather: instruction issue, transforms: FP64 pipe, exchange: shared memory + pair barriers, from_torus: the conversion unit):
 //
 //   * Accumulator convention G = -acc, the same 64-bit word in TMEM (home layout) and in the shared-memory rotation
 //     copy; the rounding/bias constant C = 2^63 - 2^40 of the exact digit (decomposer.rs:98-116, iter.rs:120-127) is an
@@ -20,7 +26,7 @@
 //     sibling to finish reading: the two pair barriers of a step are split arrive / wait mbarriers whose arrive sits
 //     a full 32-point transform before the matching wait.
 #pragma once
-#include "pbs_kernel3.cuh"
+#include "pbs_common.cuh"
 
 namespace b200 {
 

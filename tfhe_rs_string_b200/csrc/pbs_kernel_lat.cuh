@@ -1,5 +1,5 @@
 // pbs_kernel_lat.cuh -- latency variant of the programmable bootstrap for small batches (same contract
-// and reference citations as pbs_kernel.cuh / pbs_kernel3.cuh).
+// and reference citations as pbs_kernel5.cuh).
 //
 // A CMUX step is a serial dependency chain per polynomial; with one warp per polynomial that chain
 // is 14 k cycles.  Here a polynomial gets TWO warps (warps q and q + 4, same TMEM quadrant q): thread
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
         for (int i = 0; i < a.n; i++) {
             PBS3_TS(0);
             double xr[16], xi[16];
-            // phase A: ct1 = acc * X^a~ - acc, round + digit, exact int -> double, twist by C_m (see pbs_kernel3.cuh)
+            // phase A: ct1 = acc * X^a~ - acc, round + digit, exact int -> double, twist by C_m (see pbs_kernel5.cuh)
             {
                 // group-uniform gather of pbs_kernel5.cuh: this thread's slots 16 h .. 16 h + 15 of either half are two groups of 8
                 const uint32_t q0 = (4096u - (uint32_t)ahat[i]) & 4095u;

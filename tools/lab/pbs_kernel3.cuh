@@ -18,64 +18,10 @@
 //   * from_torus scales by 2^64 with an exponent add instead of a DMUL (the FP64 pipe is the
 //     binding resource).
 #pragma once
-#include "pbs_common.cuh"
+#include "../../tfhe_rs_string_b200/csrc/pbs_common.cuh"
 
 namespace b200 {
 
-constexpr uint64_t kAccC = 0x7FFFFF0000000000ull;     // C = 2^63 - 2^40
-constexpr uint32_t kTmemAcc0 = 128, kTmemXchg = 384;   // column offsets inside a quadrant
-
-// ---- TMEM accessors without a "memory" clobber: ordering is carried by the register operands, so
-// the compiler stays free to schedule shared-memory loads across them.
-__device__ __forceinline__ void tmem_ld16_nc(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
-}
-__device__ __forceinline__ void tmem_st16_nc(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-                 :
-                 : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
-}
-
-__device__ __forceinline__ double dbl(const uint32_t lo, const uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
-__device__ __forceinline__ void undbl(const double d, uint32_t &lo, uint32_t &hi) {
-    lo = (uint32_t)__double2loint(d); hi = (uint32_t)__double2hiint(d);
-}
-
-// from_torus (torus/mod.rs:72-78; round-half-even like fft/x86.rs:864): fractional part centred at
-// 0, times 2^64 by adding 64 to the exponent field (f is 0 or |f| >= 2^-1022; +-0 / subnormal
-// inputs become < 2^-950 and convert to 0), rounded to i64.  (Measured: replacing the F2I by an
-// all-FP64 split conversion does not shorten the phase.)
-__device__ __forceinline__ uint64_t from_torus_exp(const double x) {
-    const double f = x - rint(x);
-    const double s = __hiloint2double(__double2hiint(f) + (64 << 20), __double2loint(f));
-#ifdef B200TFHE_LAB_NOSAT
-    // development (tools/lab): a fractional part of exactly +1/2 gives 2^63 instead of the saturated 2^63 - 1, so that
-    // pbs_kernel5 (whose from_torus does not saturate) can be compared bit for bit
-    if (s == 9223372036854775808.0) return 0x8000000000000000ull;
-#endif
-    return (uint64_t)__double2ll_rn(s);
-}
-
-// Development aid (tools/timeline.py): compile with -DB200TFHE_TIMELINE to record per-warp phase
-// timestamps of CTA 0, CMUX steps 100..107, into PbsArgs::dbg.
-#ifdef B200TFHE_TIMELINE
-#define PBS3_TS(k) do { if (a.dbg && blockIdx.x == 0 && lane == 0 && i >= 100 && i < 108) a.dbg[((i - 100) * 8 + warp) * 16 + (k)] = clock64(); } while (0)
-#else
-#define PBS3_TS(k) do { } while (0)
-#endif
-// Development aid (tools/lab): compile with -DB200TFHE_DUMP to record, for CTA 0 and the last CMUX step, every lane's digits,
-// inverse-transform outputs and torus increments into PbsArgs::dbg ([warp][m][lane][6]).
-#ifdef B200TFHE_DUMP
-#define PBS_DUMP(k, v) do { if (a.dbg && blockIdx.x == 0 && i == a.n - 1) a.dbg[(((size_t)warp * 32 + m) * 32 + lane) * 6 + (k)] = (long long)(v); } while (0)
-#else
-#define PBS_DUMP(k, v) do { } while (0)
-#endif
 // kCts3 ciphertexts per CTA: 4 for throughput; 1..3 for small batches (fewer warps per SM sub-partition
 // shorten the per-step critical path, see launch_pbs3), always one CTA per SM.
 template <int kCts3>
@@ -89,9 +35,6 @@ __host__ __device__ constexpr size_t pbs3_smem_bytes() {
 // Every phase of a CMUX step is bound by a different unit (gather: integer ALU + instruction fetch, transforms: FP64
 // pipe, exchange/multiply: shared memory, from_torus: conversion unit), so the two warps of a sub-partition then
 // always ask for different units.  Hand-over by named barriers 5 and 6 (bar.arrive / bar.sync, 256 threads).
-__device__ __forceinline__ void bar_arrive(const int id, const int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_sync_n(const int id, const int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
 template <int kCts3, int kPhase = 0>
 __global__ void __launch_bounds__(kCts3 * 64, 1) pbs_kernel3(const PbsArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];

@@ -7,7 +7,7 @@
 #include <vector>
 #include <cstring>
 #include <random>
-#include "../../tfhe_rs_string_b200/csrc/pbs_kernel3.cuh"
+#include "pbs_kernel3.cuh"
 #include "../../tfhe_rs_string_b200/csrc/pbs_kernel5.cuh"
 #include "../../tfhe_rs_string_b200/csrc/pbs_kernel_lat.cuh"
 #ifdef LAB_HAVE_K4
