@@ -58,6 +58,24 @@ def test_scalar_comparisons_all_bytes(engine, real_keys):
         assert np.array_equal(out, f(a).astype(U64)), op
 
 
+def test_encrypted_ordering_min_max(engine, real_keys):
+    # unchecked_compare_parallelized / unchecked_min_or_max_parallelized (integer/server_key/comparator.rs:383-463,849-875)
+    rng = np.random.default_rng(23)
+    n = 192
+    a = rng.integers(0, 256, n); b = rng.integers(0, 256, n)
+    b[::4] = a[::4]; b[1::8] = a[1::8] ^ 1; a[2::16] = 255; b[3::16] = 0
+    msgs = np.concatenate([blocks_of(a).ravel(), blocks_of(b).ravel()])
+    for k, (op, f) in enumerate((("radix_gt", np.greater), ("radix_lt", np.less), ("radix_ge", np.greater_equal), ("radix_le", np.less_equal))):
+        out, info = run(engine, real_keys, op, [n, 4], msgs, 630 + k)
+        assert info["depth"] == 3 and info["n_pbs"] == 4 * n    # 2 packed signs + 1 reduction + 1 map per integer
+        assert np.array_equal(out, f(a, b).astype(U64)), op
+    out, info = run(engine, real_keys, "radix_max", [n, 4], msgs, 636)
+    assert info["depth"] == 4
+    assert out.max() < 4 and np.array_equal(from_blocks(out.reshape(n, 4)), np.maximum(a, b).astype(U64))
+    out, _ = run(engine, real_keys, "radix_min", [n, 4], msgs, 637)
+    assert out.max() < 4 and np.array_equal(from_blocks(out.reshape(n, 4)), np.minimum(a, b).astype(U64))
+
+
 def test_config3_string_eq_and_uppercase(engine, real_keys):
     rng = np.random.default_rng(22)
     n, L = 16, 64

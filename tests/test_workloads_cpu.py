@@ -52,6 +52,27 @@ def test_radix_eq_add_sub_cleartext():
     assert d.max() < 4 and np.array_equal(from_blocks(d), ((a - b) % 256).astype(np.uint64))
 
 
+def test_encrypted_ordering_min_max_cleartext():
+    """unchecked_compare_parallelized / unchecked_min_or_max_parallelized (integer/server_key/comparator.rs:383-463,849-875):
+    every pair of a small exhaustive grid plus random bytes, against Python's operators."""
+    rng = np.random.default_rng(5)
+    g = np.array([0, 1, 3, 4, 15, 16, 17, 63, 64, 127, 128, 200, 254, 255])
+    a = np.concatenate([np.repeat(g, len(g)), rng.integers(0, 256, 400)])
+    b = np.concatenate([np.tile(g, len(g)), rng.integers(0, 256, 400)])
+    n = len(a)
+    inp = np.concatenate([blocks_of(a).ravel(), blocks_of(b).ravel()])
+    for op, f in (("radix_gt", np.greater), ("radix_lt", np.less), ("radix_ge", np.greater_equal), ("radix_le", np.less_equal)):
+        assert np.array_equal(O.circuit_run_cleartext(op, [n, 4], inp), f(a, b).astype(np.uint64)), op
+    mx = O.circuit_run_cleartext("radix_max", [n, 4], inp).reshape(n, 4)
+    mn = O.circuit_run_cleartext("radix_min", [n, 4], inp).reshape(n, 4)
+    assert mx.max() < 4 and np.array_equal(from_blocks(mx), np.maximum(a, b).astype(np.uint64))
+    assert mn.max() < 4 and np.array_equal(from_blocks(mn), np.minimum(a, b).astype(np.uint64))
+    # odd block counts leave the top block unpacked (comparator.rs:430-443 chunks of 2)
+    a3, b3 = a % 64, b % 64
+    inp3 = np.concatenate([blocks_of(a3)[:, :3].ravel(), blocks_of(b3)[:, :3].ravel()])
+    assert np.array_equal(O.circuit_run_cleartext("radix_gt", [n, 3], inp3), (a3 > b3).astype(np.uint64))
+
+
 @pytest.mark.parametrize("scalar", [0, 1, 96, 123, 200, 255, 256, 1000])
 def test_scalar_comparisons_cleartext(scalar):
     a = np.arange(256)
@@ -118,6 +139,9 @@ def test_workloads_encrypted_on_toy_parameters(toy_keys):
     a = rng.integers(0, 256, 6); b = rng.integers(0, 256, 6); b[:2] = a[:2]
     cts = toy_keys.encrypt_batch(np.concatenate([blocks_of(a).ravel(), blocks_of(b).ravel()]), seed=50)
     assert list(toy_keys.decrypt_batch(O.circuit_run_encrypted(toy_keys, "radix_eq", [6, 4], cts))) == list((a == b).astype(int))
+    assert list(toy_keys.decrypt_batch(O.circuit_run_encrypted(toy_keys, "radix_gt", [6, 4], cts))) == list((a > b).astype(int))
+    mx = toy_keys.decrypt_batch(O.circuit_run_encrypted(toy_keys, "radix_max", [6, 4], cts)).reshape(6, 4)
+    assert np.array_equal(from_blocks(mx), np.maximum(a, b).astype(np.uint64))
     s = toy_keys.decrypt_batch(O.circuit_run_encrypted(toy_keys, "radix_add", [6, 4], cts)).reshape(6, 4)
     assert np.array_equal(from_blocks(s), ((a + b) % 256).astype(np.uint64))
     text = ["Hello, FHE world {z}~`a"]

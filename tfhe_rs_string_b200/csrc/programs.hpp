@@ -15,6 +15,10 @@ namespace b200 {
 //   radix_ne        shape {n_ints, n_blocks}            in: lhs, rhs                                         out: n_ints booleans
 //   radix_bitand / radix_bitor / radix_bitxor
 //                   shape {n_ints, n_blocks}            in: lhs, rhs                                         out: result[n_ints][n_blocks]
+//   radix_gt / radix_lt / radix_ge / radix_le (encrypted vs encrypted, unsigned)
+//                   shape {n_ints, n_blocks}            in: lhs, rhs                                         out: n_ints booleans
+//   radix_max / radix_min
+//                   shape {n_ints, n_blocks}            in: lhs, rhs                                         out: result[n_ints][n_blocks]
 //   radix_shl       shape {n_ints, n_blocks, bits}      in: lhs                                              out: (lhs << bits)[n_ints][n_blocks]
 //   radix_scalar_gt / radix_scalar_lt / radix_scalar_le / radix_scalar_ge / radix_scalar_eq
 //                   shape {n_ints, n_blocks, scalar}    in: lhs                                              out: n_ints booleans
@@ -39,7 +43,8 @@ inline std::unique_ptr<Circuit> build_program(const std::string &op, const std::
         return r;
     };
     if (op == "radix_eq" || op == "radix_ne" || op == "radix_add" || op == "radix_sub" || op == "radix_bitand" ||
-        op == "radix_bitor" || op == "radix_bitxor") {
+        op == "radix_bitor" || op == "radix_bitxor" || op == "radix_gt" || op == "radix_lt" || op == "radix_ge" ||
+        op == "radix_le" || op == "radix_max" || op == "radix_min") {
         need(2);
         const size_t n = shape[0], nb = shape[1];
         cp.reset(new Circuit(msg_mod, carry_mod, 2 * n * nb));
@@ -48,7 +53,13 @@ inline std::unique_ptr<Circuit> build_program(const std::string &op, const std::
             Radix a = radix_at(c, i * nb, nb), b = radix_at(c, (n + i) * nb, nb);
             if (op == "radix_eq") c.output(radix_eq(c, a, b));
             else if (op == "radix_ne") c.output(radix_ne(c, a, b));
-            else {
+            else if (op == "radix_gt") c.output(radix_gt(c, a, b));
+            else if (op == "radix_lt") c.output(radix_lt(c, a, b));
+            else if (op == "radix_ge") c.output(radix_ge(c, a, b));
+            else if (op == "radix_le") c.output(radix_le(c, a, b));
+            else if (op == "radix_max" || op == "radix_min") {
+                for (const Lin &blk : radix_min_max(c, a, b, op == "radix_max")) c.output(blk);
+            } else {
                 Radix r = op == "radix_add" ? radix_add(c, a, b) : op == "radix_sub" ? radix_sub(c, a, b)
                         : radix_bitop(c, a, b, op == "radix_bitand" ? '&' : op == "radix_bitor" ? '|' : '^');
                 for (const Lin &blk : r) c.output(blk);
@@ -154,8 +165,8 @@ struct ProgramLayout {
 inline ProgramLayout program_layout(const std::string &op, const std::vector<uint64_t> &shape) {
     ProgramLayout l;
     auto at = [&](size_t i) { return i < shape.size() ? (size_t)shape[i] : (size_t)0; };
-    if (op == "radix_eq" || op == "radix_ne") { l = {true, at(0), {at(1), at(1)}, 1}; }
-    else if (op == "radix_add" || op == "radix_sub" || op == "radix_bitand" || op == "radix_bitor" || op == "radix_bitxor") { l = {true, at(0), {at(1), at(1)}, at(1)}; }
+    if (op == "radix_eq" || op == "radix_ne" || op == "radix_gt" || op == "radix_lt" || op == "radix_ge" || op == "radix_le") { l = {true, at(0), {at(1), at(1)}, 1}; }
+    else if (op == "radix_add" || op == "radix_sub" || op == "radix_bitand" || op == "radix_bitor" || op == "radix_bitxor" || op == "radix_max" || op == "radix_min") { l = {true, at(0), {at(1), at(1)}, at(1)}; }
     else if (op == "radix_shl") { l = {true, at(0), {at(1)}, at(1)}; }
     else if (op.rfind("radix_scalar_", 0) == 0) { l = {true, at(0), {at(1)}, 1}; }
     else if (op == "string_eq" || op == "string_ne" || op == "string_starts_with" || op == "string_ends_with") { l = {true, at(0), {at(1) * at(3), at(2) * at(3)}, 1}; }

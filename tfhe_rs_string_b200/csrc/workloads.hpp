@@ -233,6 +233,52 @@ inline Lin scalar_gt(Circuit &c, const Radix &a, uint64_t s) { return scalar_cmp
 inline Lin scalar_lt(Circuit &c, const Radix &a, uint64_t s) { return scalar_cmp(c, a, s, [](uint64_t x) { return x == kInf; }); }
 inline Lin scalar_le(Circuit &c, const Radix &a, uint64_t s) { return scalar_cmp(c, a, s, [](uint64_t x) { return x != kSup; }); }
 inline Lin scalar_ge(Circuit &c, const Radix &a, uint64_t s) { return scalar_cmp(c, a, s, [](uint64_t x) { return x != kInf; }); }
+// ---- encrypted / encrypted ordering (integer/server_key/comparator.rs)
+// unchecked_compare_parallelized for unsigned radix integers, comparator.rs:383-463: blocks packed in pairs
+// (pack_block_chunk, needs carry_modulus >= message_modulus), compare_block_assign :191-220 = TRUE LWE subtraction
+// (a negative difference sets the padding bit, the sign table then yields -1 mod), sign table, +1 -> {0, 1, 2};
+// then reduce_signs_parallelized
+inline Lin radix_sign(Circuit &c, const Radix &a, const Radix &b) {
+    if (a.size() != b.size() || a.empty()) throw std::invalid_argument("radix_sign: operands need the same, non-zero block count");
+    if (c.carry_mod < c.msg_mod) throw std::invalid_argument("radix_sign: block packing needs carry_modulus >= message_modulus");
+    const int sign_lut = c.lut([](uint64_t x) { return (uint64_t)(x != 0); });
+    std::vector<Lin> signs;
+    for (size_t i = 0; i < a.size(); i += 2) {
+        const bool pair = i + 1 < a.size();
+        const Lin pa = pair ? c.axpy(a[i + 1], c.msg_mod, a[i], 1) : a[i];
+        const Lin pb = pair ? c.axpy(b[i + 1], c.msg_mod, b[i], 1) : b[i];
+        // the difference lies in (-modulus_sup, modulus_sup): deliberately through the padding bit, hence pbs_unchecked
+        signs.push_back(c.add_const(c.pbs_unchecked(c.sub(pa, pb), sign_lut, 1), 1));
+        signs.back().degree = 2;
+    }
+    return reduce_signs(c, signs);
+}
+// map_sign_result (comparator.rs:957-971): gt / lt / ge / le as one more lookup on the sign block
+inline Lin radix_cmp(Circuit &c, const Radix &a, const Radix &b, const std::function<bool(uint64_t)> &pred) {
+    return c.pbs(radix_sign(c, a, b), c.lut([pred](uint64_t x) { return (uint64_t)pred(x); }));
+}
+inline Lin radix_gt(Circuit &c, const Radix &a, const Radix &b) { return radix_cmp(c, a, b, [](uint64_t x) { return x == kSup; }); }
+inline Lin radix_lt(Circuit &c, const Radix &a, const Radix &b) { return radix_cmp(c, a, b, [](uint64_t x) { return x == kInf; }); }
+inline Lin radix_ge(Circuit &c, const Radix &a, const Radix &b) { return radix_cmp(c, a, b, [](uint64_t x) { return x != kInf; }); }
+inline Lin radix_le(Circuit &c, const Radix &a, const Radix &b) { return radix_cmp(c, a, b, [](uint64_t x) { return x != kSup; }); }
+// unchecked_min_or_max_parallelized, comparator.rs:849-875 -> unchecked_programmable_if_then_else_parallelized
+// (radix_parallel/cmux.rs:194-248): both operands are zeroed block by block with a bivariate lookup on (block, sign)
+// under the predicate / its negation, added, and cleaned with message_extract
+inline Radix radix_min_max(Circuit &c, const Radix &a, const Radix &b, bool want_max) {
+    const Lin sign = radix_sign(c, a, b);
+    const uint32_t factor = 3;   // sign block in {0, 1, 2}: factor = degree + 1
+    const uint64_t keep_a = want_max ? kSup : kInf;   // a is kept when it is the strict winner, b otherwise (ties: b = a)
+    const int lut_a = c.lut_bivariate([keep_a](uint64_t blk, uint64_t sg) { return sg == keep_a ? blk : (uint64_t)0; }, factor);
+    const int lut_b = c.lut_bivariate([keep_a](uint64_t blk, uint64_t sg) { return sg == keep_a ? (uint64_t)0 : blk; }, factor);
+    const int clean = lut_message_extract(c);
+    Radix r(a.size());
+    for (size_t i = 0; i < a.size(); i++) {
+        const Lin ta = c.pbs_bivariate(a[i], sign, lut_a, factor), tb = c.pbs_bivariate(b[i], sign, lut_b, factor);
+        r[i] = c.pbs(c.add(ta, tb), clean);
+    }
+    return r;
+}
+
 // unchecked_scalar_eq_parallelized, radix_parallel/scalar_comparison.rs:230-330: per pair of blocks one PBS
 // "packed == packed scalar", then all-true
 inline Lin scalar_eq(Circuit &c, const Radix &a, uint64_t scalar) {
