@@ -83,6 +83,19 @@ __device__ __forceinline__ void sts_v2(uint64_t *p, const uint32_t lo, const uin
 #ifndef PBS5_ORDER
 #define PBS5_ORDER 0
 #endif
+// 4 ciphertexts per CTA: the two warps of a ciphertext are warps w and w + 4, i.e. they share an SM sub-partition and a TMEM
+// quadrant (measured: 1.2 % faster than warps 2c and 2c + 1 -- the pair then runs in lock step on one scheduler).  They
+// could then hand the first kXtQ frequency blocks of their transforms over through the 128 tensor-memory columns the
+// quadrant has left (64 per direction) instead of shared memory; measured slower (kXtQ = 8: +2 %, 16: +8 % time: the
+// TMEM store / fence / load chain sits on the critical path of the hand-over), so kXtQ = 0.
+#ifndef PBS5_XT
+#define PBS5_XT 1
+#endif
+#ifndef PBS5_XTQ
+#define PBS5_XTQ 0
+#endif
+constexpr int kXtQ = PBS5_XTQ;             // frequency blocks q < kXtQ travel through TMEM
+constexpr uint32_t kTmemXt0 = 384;         // column offset of the two 64-column exchange areas
 __host__ __device__ constexpr int slot5(const int c, const int k) { return PBS5_ORDER ? brev5(4 * c + k) : 4 * c + k; }
 
 // stages [kFirst, kLast] (butterfly distance 2^stage) of the in-register 32-point DIT transform of fft.cuh
@@ -113,45 +126,50 @@ __device__ __forceinline__ void fft32_dit_df(double (&xr)[32], double (&xi)[32],
     }
 }
 // z[r] += B[1-p][p][q] * F_sibling[q] for the frequency block q = brev5(r) that register r of the inverse transform holds
+template <bool kXT>
 struct SiblingProduct {
     const double2 *b_oth, *f_oth;   // both already offset by the lane
+    const uint32_t (*xt)[16];       // kXT: the sibling's blocks q < kXtQ as read from TMEM (4 blocks per 16 words)
     template <int kR>
     __device__ __forceinline__ void run(double (&zr)[32], double (&zi)[32]) const {
         constexpr int q = brev5(kR);
-        const double2 bx = b_oth[q * 32], g = f_oth[q * 32];
+        const double2 bx = b_oth[q * 32];
+        double2 g;
+        if constexpr (kXT && q < kXtQ) g = make_double2(dbl(xt[q / 4][4 * (q % 4)], xt[q / 4][4 * (q % 4) + 1]), dbl(xt[q / 4][4 * (q % 4) + 2], xt[q / 4][4 * (q % 4) + 3]));
+        else g = f_oth[q * 32];
         const double o_r = fma(bx.x, g.x, zr[kR]), o_i = fma(bx.x, g.y, zi[kR]);
         zr[kR] = fma(-bx.y, g.y, o_r); zi[kR] = fma(bx.y, g.x, o_i);
     }
 };
-template <int kR>
-__device__ __forceinline__ void sibling_products(double (&zr)[32], double (&zi)[32], const SiblingProduct &oth) {
+template <int kR, bool kXT>
+__device__ __forceinline__ void sibling_products(double (&zr)[32], double (&zi)[32], const SiblingProduct<kXT> &oth) {
     if constexpr (kR < 32) {
         oth.template run<kR>(zr, zi);
-        sibling_products<kR + 1>(zr, zi, oth);
+        sibling_products<kR + 1, kXT>(zr, zi, oth);
     }
 }
-template <int kQ>
+template <int kQ, bool kXT = false>
 __device__ __forceinline__ void own_product(double (&zr)[32], double (&zi)[32], const double (&xr)[32], const double (&xi)[32],
                                             const double2 *b_own, double2 *f_dst) {
-    f_dst[kQ * 32] = make_double2(xr[kQ], xi[kQ]);
+    if constexpr (!(kXT && kQ < kXtQ)) f_dst[kQ * 32] = make_double2(xr[kQ], xi[kQ]);
     const double2 bo = b_own[kQ * 32];
     zr[brev5(kQ)] = fma(-bo.y, xi[kQ], bo.x * xr[kQ]);
     zi[brev5(kQ)] = fma(bo.y, xr[kQ], bo.x * xi[kQ]);
 }
-template <int kQ, bool kFused>
+template <int kQ, bool kFused, bool kXT = false>
 __device__ __forceinline__ void own_products(double (&zr)[32], double (&zi)[32], double (&xr)[32], double (&xi)[32],
                                              const double2 *b_own, double2 *f_dst) {
     if constexpr (kFused) {
         if constexpr (kQ < 16) {
             bfly<false>(xr[kQ], xi[kQ], xr[kQ + 16], xi[kQ + 16], kQ);   // last stage: outputs kQ and kQ + 16 are final
-            own_product<kQ>(zr, zi, xr, xi, b_own, f_dst);
-            own_product<kQ + 16>(zr, zi, xr, xi, b_own, f_dst);
-            own_products<kQ + 1, kFused>(zr, zi, xr, xi, b_own, f_dst);
+            own_product<kQ, kXT>(zr, zi, xr, xi, b_own, f_dst);
+            own_product<kQ + 16, kXT>(zr, zi, xr, xi, b_own, f_dst);
+            own_products<kQ + 1, kFused, kXT>(zr, zi, xr, xi, b_own, f_dst);
         }
     } else {
         if constexpr (kQ < 32) {
-            own_product<kQ>(zr, zi, xr, xi, b_own, f_dst);
-            own_products<kQ + 1, kFused>(zr, zi, xr, xi, b_own, f_dst);
+            own_product<kQ, kXT>(zr, zi, xr, xi, b_own, f_dst);
+            own_products<kQ + 1, kFused, kXT>(zr, zi, xr, xi, b_own, f_dst);
         }
     }
 }
@@ -163,7 +181,7 @@ __device__ __forceinline__ void own_products(double (&zr)[32], double (&zi)[32],
 #endif
 
 #ifdef B200TFHE_LAB_DELAY
-__device__ int g_lab_delay;   // development (tools/lab): warps 4-7 enter the CMUX loop this many cycles late
+__device__ int g_lab_delay;   // development (tools/lab): the warps of ciphertext c enter the CMUX loop c * g_lab_delay cycles late
 #endif
 
 // kPhase = 1 (4 full ciphertexts per CTA only): the two halves of the CTA run HALF A STEP apart.  Warps 0-3 ("early") and
@@ -175,8 +193,9 @@ __device__ int g_lab_delay;   // development (tools/lab): warps 4-7 enter the CM
 template <int kCts, int kPhase = 0>
 __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr bool kXT = PBS5_XT && kCts == 4 && kPhase == 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ctl = warp >> 1, p = warp & 1;
+    const int ctl = kXT ? (warp & 3) : (warp >> 1), p = kXT ? (warp >> 2) : (warp & 1);
     const int ct = blockIdx.x * kCts + ctl;
     const bool active = ct < a.batch;
 
@@ -209,6 +228,7 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
     const uint32_t tbase = *slot;
     const uint32_t tquad = tbase + (((uint32_t)(warp & 3) * 32u) << 16);
     const uint32_t t_acc = tquad + kTmemAcc0 + (uint32_t)(warp >> 2) * 128u;
+    const uint32_t t_xt_out = tquad + kTmemXt0 + (uint32_t)p * 64u, t_xt_in = tquad + kTmemXt0 + (uint32_t)(1 - p) * 64u;   // kXT only
     const TmemTwiddles tw{tquad};
     if (warp < 4) {   // one warp per TMEM quadrant stores its lanes' twiddle columns
 #pragma unroll
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
         ct_barrier(1 + ctl);  // a~ table visible to both warps; rotation copy visible within the warp
 
 #ifdef B200TFHE_LAB_DELAY
-        if (warp >= 4) { const long long t_in = clock64(); while (clock64() - t_in < g_lab_delay) { } }
+        { const long long t_in = clock64(); while (clock64() - t_in < (long long)g_lab_delay * ctl) { } }   // ciphertext c starts c * delay cycles late
 #endif
         // ---------------------------------------------------------------- CMUX loop
         // Steps with a~ = 0 (mod 2N) are not skipped as the reference does (bootstrap.rs:281): the rotation is then the
@@ -362,7 +382,23 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
             double zr[32], zi[32];
             {
                 const double2 *b_own = bsk_s + (size_t)(p * 2 + p) * kHalf + lane;         // row p, column p
-                own_products<0, (PBS5_FUSE & 1) != 0>(zr, zi, xr, xi, b_own, tb_sib + lane);
+                if (kXT) {   // blocks q < kXtQ of the transform go to the sibling through tensor memory
+#pragma unroll
+                    for (int c = 0; c < kXtQ / 4; c++) {
+                        uint32_t sw[16];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            undbl(xr[4 * c + k], sw[4 * k], sw[4 * k + 1]);
+                            undbl(xi[4 * c + k], sw[4 * k + 2], sw[4 * k + 3]);
+                        }
+                        tmem_st16_nc(t_xt_out + c * 16, sw);
+                    }
+                }
+                own_products<0, (PBS5_FUSE & 1) != 0, kXT>(zr, zi, xr, xi, b_own, tb_sib + lane);
+                if (kXT) {
+                    tmem_wait_st();
+                    tmem_fence_before();
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full);
@@ -375,11 +411,19 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
             PBS5_TS(6);
             {
                 const double2 *b_oth = bsk_s + (size_t)((1 - p) * 2 + p) * kHalf + lane;   // row 1-p, column p
-                const SiblingProduct oth{b_oth, tb_own + lane};
+                uint32_t xt[kXtQ / 4 + 1][16];
+                if (kXT) {
+                    tmem_fence_after();
+#pragma unroll
+                    for (int c = 0; c < kXtQ / 4; c++) tmem_ld16_nc(t_xt_in + c * 16, xt[c]);
+#pragma unroll
+                    for (int c = 0; c < kXtQ / 4; c++) tmem_wait_ld16(xt[c]);
+                }
+                const SiblingProduct<kXT> oth{b_oth, tb_own + lane, xt};
                 if (PBS5_FUSE & 2) {
                     fft32_dit_df<true, 0, 32>(zr, zi, oth);   // inverse first pass (registers only), products at the leaves
                 } else {
-                    sibling_products<0>(zr, zi, oth);
+                    sibling_products<0, kXT>(zr, zi, oth);
                     inv1024_pass1(zr, zi);
                 }
             }
