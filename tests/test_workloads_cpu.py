@@ -107,6 +107,12 @@ def test_string_eq_cleartext_config3_shape():
     # different clear lengths: never equal for unpadded strings (comparisons.rs:195-212)
     out = O.circuit_run_cleartext("string_eq", [1, 3, 2, 4], np.concatenate([chars(["abc"]).ravel(), chars(["ab"]).ravel()]))
     assert list(out) == [0]
+    # Padding::Final (zero characters after the content, eq_encrypted -> eq_no_init_padding, comparisons.rs:101-124,184-215):
+    # the same content behind different amounts of padding is equal, an extra character is not
+    for sa, sb, want in (("abc\0\0", "abc\0\0", 1), ("abc\0\0", "abc", 1), ("abc", "abc\0\0\0", 1), ("abcd\0", "abc", 0),
+                         ("abc\0\0", "abd\0\0", 0), ("\0\0", "\0\0\0", 1), ("ab\0\0", "abc\0", 0)):
+        out = O.circuit_run_cleartext("string_eq", [1, len(sa), len(sb), 4], np.concatenate([chars([sa]).ravel(), chars([sb]).ravel()]))
+        assert list(out) == [want], (sa, sb)
 
 
 @pytest.mark.parametrize("hay,pat", [("the quick brown fox jumps over the lazy dog", "brown"), ("aaaaaaaab", "aab"), ("abc", "abcd"),
