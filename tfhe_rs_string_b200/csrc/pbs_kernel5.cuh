@@ -91,6 +91,10 @@ __device__ __forceinline__ void sts_v2(uint64_t *p, const uint32_t lo, const uin
 #ifndef PBS5_XT
 #define PBS5_XT 1
 #endif
+// digit -> double: 0 = exponent trick + DADD (FP64 pipe), 1 = I2F.F64.S32 (conversion unit), 2 = half and half
+#ifndef PBS5_I2F
+#define PBS5_I2F 0
+#endif
 #ifndef PBS5_XTQ
 #define PBS5_XTQ 0
 #endif
@@ -323,8 +327,12 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                         const uint64_t e1 = pack64(h[4 * mm + 2], h[4 * mm + 3]) + (r1 ^ pack64(ti, ti)) + pack64(ti & 1u, 0x7FFFFF00u);
                         const uint32_t d0 = (uint32_t)(e0 >> 41), d1 = (uint32_t)(e1 >> 41);
                         // digit + (2^22 - 1) in [0, 2^23) -> double by exponent trick (exact)
+#if PBS5_I2F
+                        double fr = (double)((int)d0 - 4194303), fi = (double)((int)d1 - 4194303);   // conversion unit instead of the FP64 pipe
+#else
                         double fr = dbl(d0, 0x43300000u) - 4503599631564799.0;
                         double fi = dbl(d1, 0x43300000u) - 4503599631564799.0;
+#endif
                         PBS_DUMP(0, d0); PBS_DUMP(1, d1);
                         twist_m(fr, fi, m);
                         xr[brev5(m)] = fr; xi[brev5(m)] = fi;
