@@ -173,7 +173,7 @@ int b200tfhe_kernel_launch_count(b200tfhe_ctx *ctx, uint64_t *count);
  * contains,find}.rs; apps/trivium/src/trivium/trivium_bool.rs:143-227).  A program is that schedule
  * compiled once for a workload shape: per level ONE lwe-linear launch + ONE ks_pbs_batch launch, all
  * intermediate blocks resident in HBM.  Names and shapes: tfhe_rs_string_b200/csrc/programs.hpp
- * ("radix_eq|ne|add|sub|bitand|bitor|bitxor|shl", "radix_scalar_gt|lt|le|ge|eq",
+ * ("radix_eq|ne|gt|lt|ge|le|max|min|add|sub|bitand|bitor|bitxor|shl", "radix_scalar_gt|lt|le|ge|eq",
  * "string_eq|ne|starts_with|ends_with|to_uppercase|to_lowercase|contains|find", "trivium").  Inputs and outputs are
  * arrays of big-key LWE blocks (k*N+1 u64 each). */
 typedef struct b200tfhe_program b200tfhe_program;
