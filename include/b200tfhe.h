@@ -229,6 +229,10 @@ int b200tfhe_debug_negacyclic_mul(b200tfhe_ctx *ctx, const uint64_t *a_int, cons
  * 2^42); mirrors fft_impl/common.rs:145-304, which tests the bootstrap against its definition. */
 int b200tfhe_debug_pbs_steps(b200tfhe_ctx *ctx, const uint64_t *in_small, const uint32_t *lut_id, uint64_t *out,
                              size_t batch, uint32_t steps);
+/* from_torus (core_crypto/commons/math/torus/mod.rs:72-78, round-half-even as in fft/x86.rs:864) of n doubles, |x| < 2^37,
+ * by the two device routines: out_fp = the FP64-pipe conversion the bootstrap kernels use, out_cvt = x - rint(x), times
+ * 2^64, cvt.rni.s64.  Host buffers. */
+int b200tfhe_debug_from_torus(b200tfhe_ctx *ctx, const double *x, uint64_t *out_fp, uint64_t *out_cvt, size_t n);
 
 #ifdef __cplusplus
 }

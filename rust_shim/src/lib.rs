@@ -129,6 +129,7 @@ extern "C" {
     pub fn b200tfhe_program_run_device(prog: *mut b200tfhe_program, d_in: *const u64, d_out: *mut u64) -> c_int;
     pub fn b200tfhe_program_destroy(prog: *mut b200tfhe_program) -> c_int;
     pub fn b200tfhe_debug_negacyclic_mul(ctx: *mut b200tfhe_ctx, a_int: *const u64, b_torus: *const u64, out: *mut u64, count: usize) -> c_int;
+    pub fn b200tfhe_debug_from_torus(ctx: *mut b200tfhe_ctx, x: *const f64, out_fp: *mut u64, out_cvt: *mut u64, n: usize) -> c_int;
 }
 
 #[derive(Debug)]

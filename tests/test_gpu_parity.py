@@ -64,6 +64,32 @@ def test_keyswitch_adversarial_inputs(engine, real_keys):
 
 
 # batch -> kernel chosen by the launcher on a 148-SM part (b200tfhe.cu:launch_pbs_fast): 40 -> pbs_lat_kernel<1>,
+def test_from_torus_fp_pipe_is_exact(engine):
+    """The bootstrap kernels' from_torus (two exponent-aligned additions + one fused multiply-add, pbs_common.cuh) against exact
+    rational arithmetic: round_half_even(frac(x) * 2^64) mod 2^64 (torus/mod.rs:72-78, fft/x86.rs:864) for magnitudes 2^-80 .. 2^36,
+    ties and half-integers included; the rint + cvt.rni routine differs from it only where it saturates (+1/2 -> 2^63 - 1)."""
+    from fractions import Fraction
+    rng = np.random.default_rng(7)
+    xs = [0.0, -0.0, 0.5, -0.5, 1.5, 2.5, -3.5, 2.0 ** -65, 3 * 2.0 ** -66, -5 * 2.0 ** -66, 12345.5, 2.0 ** 36 + 0.5, -(2.0 ** 36) + 0.25]
+    for e in range(-80, 37):
+        xs += list(rng.uniform(-1, 1, 40) * 2.0 ** e)
+    xs += list(np.round(rng.uniform(-2 ** 30, 2 ** 30, 500) * 2 ** 20) / 2 ** 20 + 0.5)   # many exact half-way cases
+    xs = np.array(xs, dtype=np.float64)
+    fp, cvt = engine.debug_from_torus(xs)
+
+    def exact(x):
+        f = Fraction(float(x)) * (1 << 64)
+        fl = f.numerator // f.denominator
+        rem = f - fl
+        if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and fl % 2 == 1):
+            fl += 1
+        return fl % (1 << 64)
+    want = np.array([exact(x) for x in xs], dtype=U64)
+    assert np.array_equal(fp, want)
+    diff = cvt != want
+    assert np.all(want[diff] == U64(1 << 63)) and np.all(cvt[diff] == U64((1 << 63) - 1))
+
+
 # 200 -> pbs_lat_kernel<2>, 400 -> pbs_kernel5<3>, 500 -> pbs_kernel5<4> (one wave), 1024 -> pbs_kernel5<4> (two waves,
 # BASELINE configs[0]): the throughput kernel that the benchmark times is compared with the oracle like the others.
 @pytest.mark.parametrize("batch", [40, 200, 400, 500, 1024])

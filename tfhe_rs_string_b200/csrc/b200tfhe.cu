@@ -1307,6 +1307,29 @@ int b200tfhe_debug_negacyclic_mul(b200tfhe_ctx *ctx, const uint64_t *a_int, cons
     return 0;
 }
 
+int b200tfhe_debug_from_torus(b200tfhe_ctx *ctx, const double *x, uint64_t *out_fp, uint64_t *out_cvt, size_t n) {
+    if (int rc = check_ready(ctx)) return rc;
+    std::lock_guard<std::mutex> l(ctx->mu);
+    if (n == 0) return 0;
+    ARG_TRY(ctx, x && out_fp && out_cvt, "null pointer");
+    DevCtx &d = *ctx->devs[0];
+    double *dx = nullptr; uint64_t *da = nullptr, *db = nullptr;
+    CU_TRY(ctx, cudaMalloc(&dx, n * sizeof(double)));
+    CU_TRY(ctx, cudaMalloc(&da, n * sizeof(uint64_t)));
+    CU_TRY(ctx, cudaMalloc(&db, n * sizeof(uint64_t)));
+    cudaError_t e = cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) {
+        from_torus_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(dx, da, db, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_fp, da, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_cvt, db, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(dx); cudaFree(da); cudaFree(db);
+    CU_TRY(ctx, e);
+    return 0;
+}
+
 // One external product on caller-supplied data (unit-test hook for the Fourier stage): runs the production PBS kernel
 // selected for `batch` on the first `steps` mask elements only (lwe_dimension is taken as `steps`).
 int b200tfhe_debug_pbs_steps(b200tfhe_ctx *ctx, const uint64_t *in_small, const uint32_t *lut_id, uint64_t *out, size_t batch, uint32_t steps) {

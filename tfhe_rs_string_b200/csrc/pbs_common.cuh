@@ -40,6 +40,17 @@ __device__ __forceinline__ uint64_t from_torus_dev(double x) {
     return (uint64_t)__double2ll_rn(f * 18446744073709551616.0);
 }
 
+__device__ __forceinline__ uint64_t pack64(const uint32_t lo, const uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+constexpr uint64_t kFtBias = 0x4338000000000000ull;           // bit pattern of 1.5 * 2^52
+// from_torus on the FP64 pipe only.  |x| < 2^37.  Returns d with  round_half_even(x * 2^64) mod 2^64 = d - kFtBias.
+//   t = x + 1.5*2^38 has ulp 2^-14: its low mantissa word holds round(x * 2^14);  l = x - (t - 1.5*2^38) is exact,
+//   |l| <= 2^-15;  u = l * 2^64 + 1.5*2^52 holds round_half_even(l * 2^64) as a 52-bit two's complement mantissa.
+__device__ __forceinline__ uint64_t from_torus_fp(const double x) {
+    const double t = x + 412316860416.0;                       // 1.5 * 2^38
+    const double l = x - (t - 412316860416.0);
+    const double u = fma(l, 18446744073709551616.0, 6755399441055744.0);
+    return pack64((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u) + ((uint32_t)__double2loint(t) << 18));
+}
 // lut id of ciphertext ct; device-buffer callers cannot be validated on the host, so the range check is here
 __device__ __forceinline__ uint32_t pbs_lut_id(const PbsArgs &a, const int ct) {
     const uint32_t id = a.lut_idx ? a.lut_idx[ct] : 0u;
@@ -92,8 +103,6 @@ struct TmemTwiddles {
     __device__ __forceinline__ void issue(const int chunk, uint32_t (&r)[16]) const { tmem_ld16(taddr + chunk * 16, r); }
     __device__ __forceinline__ void wait() const { tmem_wait_ld(); }
 };
-
-__device__ __forceinline__ uint64_t pack64(const uint32_t lo, const uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 // ---- pieces shared by pbs_kernel5.cuh, pbs_kernel_lat.cuh and the regression reference tools/lab/pbs_kernel3.cuh ----
 constexpr uint64_t kAccC = 0x7FFFFF0000000000ull;     // C = 2^63 - 2^40
@@ -185,6 +194,14 @@ __global__ void __launch_bounds__(64) bsk_to_fourier_kernel(const uint64_t *__re
     }
 }
 
+// Debug/unit-test kernel: both from_torus routines on caller data
+__global__ void from_torus_test_kernel(const double *__restrict__ x, uint64_t *__restrict__ out_fp, uint64_t *__restrict__ out_cvt, const size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out_fp[i] = from_torus_fp(x[i]) - kFtBias;
+    out_cvt[i] = from_torus_dev(x[i]);
+}
+
 // Debug/unit-test kernel: out += a (x) b over Z[X]/(X^N + 1) with a taken as integer digits
 // (|a| < 2^31) and b as torus elements, through exactly the transforms the PBS uses.
 // Mirrors the reference's FFT product test (fft/tests.rs:82-222).  One warp per product.
@@ -233,8 +250,8 @@ __global__ void __launch_bounds__(32) negacyclic_mul_test_kernel(const uint64_t 
         const int j = lane + 32 * m;
         double yr = zr[m], yi = zi[m];
         untwist_m(yr, yi, m);
-        po[j] += from_torus_dev(yr);
-        po[j + kHalf] += from_torus_dev(yi);
+        po[j] += from_torus_fp(yr) - kFtBias;           // the production conversion (pbs_kernel5.cuh, pbs_kernel_lat.cuh)
+        po[j + kHalf] += from_torus_fp(yi) - kFtBias;
     }
 }
 

@@ -33,7 +33,6 @@ namespace b200 {
 constexpr int kZone5 = 256;                                   // overflow zone of the rotation copy (words)
 constexpr int kBuf5Bytes = (kN + kZone5) * 8;                 // 18,432 B per warp: rotation copy / transposition / sibling's transform
 constexpr int kHdr5Bytes = 128;                               // tmem slot @0, BSK mbarrier @8, consumer counter @16, pair mbarriers @32
-constexpr uint64_t kFtBias = 0x4338000000000000ull;           // bit pattern of 1.5 * 2^52
 static_assert(kBuf5Bytes >= kTBufElems * (int)sizeof(double2), "transposition buffer must fit");
 
 template <int kCts>
@@ -45,15 +44,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-// from_torus on the FP64 pipe only.  |x| < 2^37.  Returns d with  round_half_even(x * 2^64) mod 2^64 = d - kFtBias.
-//   t = x + 1.5*2^38 has ulp 2^-14: its low mantissa word holds round(x * 2^14);  l = x - (t - 1.5*2^38) is exact,
-//   |l| <= 2^-15;  u = l * 2^64 + 1.5*2^52 holds round_half_even(l * 2^64) as a 52-bit two's complement mantissa.
-__device__ __forceinline__ uint64_t from_torus_fp(const double x) {
-    const double t = x + 412316860416.0;                       // 1.5 * 2^38
-    const double l = x - (t - 412316860416.0);
-    const double u = fma(l, 18446744073709551616.0, 6755399441055744.0);
-    return pack64((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u) + ((uint32_t)__double2loint(t) << 18));
-}
 // G -= from_torus(x) on the two 32-bit halves of G, in three integer instructions (subtract with borrow; the bias of u
 // and the 14 top bits from t go into the high word with one multiply-add), and the rotation copy written straight from
 // the register pair the TMEM store uses.

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "b200tfhe_parse_server_key", "b200tfhe_load_server_key_bytes",
     "b200tfhe_boolean_ctx_create", "b200tfhe_boolean_ctx_destroy", "b200tfhe_boolean_last_error",
     "b200tfhe_boolean_load_ksk", "b200tfhe_boolean_load_bsk_standard", "b200tfhe_boolean_gate_batch",
-    "b200tfhe_debug_negacyclic_mul", "b200tfhe_debug_pbs_steps",
+    "b200tfhe_debug_negacyclic_mul", "b200tfhe_debug_pbs_steps", "b200tfhe_debug_from_torus",
     "b200tfhe_program_create", "b200tfhe_program_create_from_circuit", "b200tfhe_program_info", "b200tfhe_program_run", "b200tfhe_program_run_device",
     "b200tfhe_program_destroy",
 ]
@@ -138,6 +138,7 @@ def load_library():
         "b200tfhe_get_kernel_times": [ctx, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
                                       C.POINTER(C.c_uint64), C.c_int],
         "b200tfhe_debug_negacyclic_mul": [ctx, u64p, u64p, u64p, C.c_size_t],
+        "b200tfhe_debug_from_torus": [ctx, C.c_void_p, u64p, u64p, C.c_size_t],
         "b200tfhe_program_create": [ctx, C.c_char_p, u64p, C.c_size_t, C.POINTER(C.c_void_p)],
         "b200tfhe_program_info": [C.c_void_p, u64p],
         "b200tfhe_program_run": [C.c_void_p, u64p, u64p],
@@ -338,6 +339,12 @@ class Engine:
         out = np.empty((cts.shape[0], self.params.big_lwe_size), dtype=np.uint64)
         self._check(self.L.b200tfhe_debug_pbs_steps(self.h, _ptr(cts), _ptr(ids), _ptr(out), cts.shape[0], steps))
         return out
+
+    def debug_from_torus(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        a = np.empty(x.size, dtype=np.uint64); b = np.empty(x.size, dtype=np.uint64)
+        self._check(self.L.b200tfhe_debug_from_torus(self.h, x.ctypes.data_as(C.c_void_p), _ptr(a), _ptr(b), x.size))
+        return a, b
 
     def debug_negacyclic_mul(self, a_int, b_torus, out):
         a = np.ascontiguousarray(a_int, dtype=np.uint64).reshape(-1, 2048)
