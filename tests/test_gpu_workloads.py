@@ -42,7 +42,7 @@ def test_config2_uint8_eq_and_add(engine, real_keys):
     a = rng.integers(0, 256, n); b = rng.integers(0, 256, n); b[::2] = a[::2]
     msgs = np.concatenate([blocks_of(a).ravel(), blocks_of(b).ravel()])
     out, info = run(engine, real_keys, "radix_eq", [n, 4], msgs, 600)
-    assert info["n_pbs"] == 5 * n and info["depth"] == 2
+    assert info["n_pbs"] == 3 * n and info["depth"] == 2   # two packed-pair equality flags + one all-true per integer
     assert np.array_equal(out, (a == b).astype(U64))
     out, info = run(engine, real_keys, "radix_add", [n, 4], msgs, 601)
     assert np.array_equal(from_blocks(out.reshape(n, 4)), ((a + b) % 256).astype(U64))
@@ -160,7 +160,7 @@ def test_full_size_config2_1024_uint8_pairs(engine, real_keys):
     a = rng.integers(0, 256, n); b = rng.integers(0, 256, n); b[::2] = a[::2]
     msgs = np.concatenate([blocks_of(a).ravel(), blocks_of(b).ravel()])
     out, info = run(engine, real_keys, "radix_eq", [n, 4], msgs, 700)
-    assert info["n_pbs"] == 5120 and np.array_equal(out, (a == b).astype(U64))
+    assert info["n_pbs"] == 3072 and np.array_equal(out, (a == b).astype(U64))
     out, info = run(engine, real_keys, "radix_add", [n, 4], msgs, 701)
     assert np.array_equal(from_blocks(out.reshape(n, 4)), ((a + b) % 256).astype(U64))
 
@@ -173,19 +173,23 @@ def test_full_size_config3_256_strings_of_64_chars(engine, real_keys):
     for i in range(0, n, 2):   # half equal, half differing in one random position
         q = int(rng.integers(0, L)); b[i] = b[i][:q] + chr(32 + (ord(b[i][q]) - 31) % 95) + b[i][q + 1:]
     out, info = run(engine, real_keys, "string_eq", [n, L, L, 4], np.concatenate([chars(a).ravel(), chars(b).ravel()]), 710)
-    assert info["n_pbs"] == 69888 and info["depth"] == 3   # 256 x (256 block comparisons -> 16 -> 1)
+    assert info["n_pbs"] == 35072 and info["depth"] == 3   # 256 x (128 packed-pair comparisons -> 8 -> 1)
     assert list(out) == [int(x == y) for x, y in zip(a, b)]
 
 
 def test_full_size_config3_to_uppercase_256_strings(engine, real_keys):
-    """BASELINE configs[2], second half: to_uppercase on 256 strings of 64 chars (294,912 PBS, depth 7)."""
+    """BASELINE configs[2], second half: to_uppercase on 256 strings of 64 chars: 49,152 bootstraps at depth 2 with the
+    batch schedule, and the reference's own operator decomposition (294,912 bootstraps, depth 7) on the same ciphertexts."""
     rng = np.random.default_rng(33)
     n, L = 256, 64
     a = ["".join(chr(rng.integers(32, 127)) for _ in range(L)) for _ in range(n)]
     out, info = run(engine, real_keys, "string_to_uppercase", [n, L, 4], chars(a).ravel(), 711)
-    assert info["n_pbs"] == 294912
+    assert info["n_pbs"] == 49152 and info["depth"] == 2
     got = from_blocks(out.reshape(n, L, 4))
     assert ["".join(chr(int(c)) for c in row) for row in got] == [s.upper() for s in a]
+    out, info = run(engine, real_keys, "string_to_uppercase_reference", [n, L, 4], chars(a).ravel(), 711)
+    assert info["n_pbs"] == 294912 and info["depth"] == 7
+    assert np.array_equal(from_blocks(out.reshape(n, L, 4)), got)
 
 
 def test_full_size_config5_trivium_1024_bits(engine, real_keys):

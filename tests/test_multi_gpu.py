@@ -58,7 +58,7 @@ def test_multi_context_programs_split_over_units(real_keys):
         blk = lambda v: np.stack([(np.asarray(v, dtype=U64) >> U64(2 * k)) & U64(3) for k in range(4)], axis=-1).ravel()
         cts = real_keys.encrypt_batch(np.concatenate([blk(a), blk(b)]), seed=91)
         prog = T.Program(multi, "radix_eq", [n, 4])
-        assert prog.info["n_pbs"] == 5 * n
+        assert prog.info["n_pbs"] == 3 * n
         assert np.array_equal(real_keys.decrypt_batch(prog.run(cts)), (a == b).astype(U64))
         prog.close()
         prog = T.Program(multi, "radix_add", [n, 4])

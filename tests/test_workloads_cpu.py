@@ -92,6 +92,21 @@ def test_to_uppercase_every_byte_cleartext():
     assert np.array_equal(from_blocks(out), np.arange(128, 256).astype(np.uint64))
 
 
+def test_case_change_fast_schedule_equals_reference_decomposition():
+    """The 3-bootstrap schedule (case_change_char, workloads.hpp) and the reference's operator decomposition
+    (change_case.rs:53-82: two scalar comparisons, and, shift, add / sub with propagation) on every byte value."""
+    allb = blocks_of(np.arange(256)).ravel()
+    want_u = np.array([ord(chr(v).upper()) if 97 <= v <= 122 else v for v in range(256)], dtype=np.uint64)
+    want_l = np.array([v + 32 if 65 <= v <= 90 else v for v in range(256)], dtype=np.uint64)
+    for op, want in (("string_to_uppercase", want_u), ("string_to_lowercase", want_l)):
+        fast = O.circuit_run_cleartext(op, [1, 256, 4], allb).reshape(256, 4)
+        ref = O.circuit_run_cleartext(op + "_reference", [1, 256, 4], allb).reshape(256, 4)
+        assert fast.max() < 4 and np.array_equal(fast, ref) and np.array_equal(from_blocks(fast), want), op
+    assert O.circuit_info("string_to_uppercase", [1, 64, 4])["n_pbs"] == 3 * 64
+    assert O.circuit_info("string_to_uppercase", [1, 64, 4])["depth"] == 2
+    assert O.circuit_info("string_to_uppercase_reference", [1, 64, 4])["n_pbs"] == 18 * 64
+
+
 def test_string_eq_cleartext_config3_shape():
     # BASELINE configs[2]: 256 pairs of 64-char strings, half equal / half differing in one position
     rng = np.random.default_rng(3)

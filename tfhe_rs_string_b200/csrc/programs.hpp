@@ -24,7 +24,8 @@ namespace b200 {
 //                   shape {n_ints, n_blocks, scalar}    in: lhs                                              out: n_ints booleans
 //   string_eq       shape {n_str, len_a, len_b, nb}     in: a[n_str][len_a][nb], b[n_str][len_b][nb]         out: n_str booleans
 //   string_ne / string_starts_with / string_ends_with: same shape and inputs as string_eq (b is the pattern)
-//   string_to_lowercase: as string_to_uppercase
+//   string_to_lowercase: as string_to_uppercase; string_to_uppercase_reference / string_to_lowercase_reference: the same
+//                   functions through the reference's own operator decomposition (18 bootstraps per character instead of 3)
 //   string_to_uppercase shape {n_str, len, nb}          in: s[n_str][len][nb]                                out: s'[n_str][len][nb]
 //   string_contains shape {n_str, hay_len, pat_len, nb} in: hay[n_str][hay_len][nb], pat[n_str][pat_len][nb] out: n_str booleans
 //   string_find     shape {n_str, hay_len, pat_len, nb} in: hay, pat                                         out: per string: found, index[nb]
@@ -96,7 +97,8 @@ inline std::unique_ptr<Circuit> build_program(const std::string &op, const std::
             c.output(op == "string_eq" ? string_eq(c, a, b) : op == "string_ne" ? bool_not(c, string_eq(c, a, b))
                      : op == "string_starts_with" ? string_starts_with(c, a, b) : string_ends_with(c, a, b));
         }
-    } else if (op == "string_to_uppercase" || op == "string_to_lowercase") {
+    } else if (op == "string_to_uppercase" || op == "string_to_lowercase" || op == "string_to_uppercase_reference" ||
+               op == "string_to_lowercase_reference") {
         need(3);
         const size_t n = shape[0], len = shape[1], nb = shape[2];
         cp.reset(new Circuit(msg_mod, carry_mod, n * len * nb));
@@ -104,7 +106,8 @@ inline std::unique_ptr<Circuit> build_program(const std::string &op, const std::
         for (size_t s = 0; s < n; s++)
             for (size_t i = 0; i < len; i++) {
                 Radix ch = radix_at(c, (s * len + i) * nb, nb);
-                Radix r = op == "string_to_uppercase" ? to_uppercase_char(c, ch) : to_lowercase_char(c, ch);
+                Radix r = op == "string_to_uppercase" ? to_uppercase_char(c, ch) : op == "string_to_lowercase" ? to_lowercase_char(c, ch)
+                        : op == "string_to_uppercase_reference" ? to_uppercase_char_reference(c, ch) : to_lowercase_char_reference(c, ch);
                 for (const Lin &blk : r) c.output(blk);
             }
     } else if (op == "string_contains" || op == "string_find") {
@@ -170,7 +173,7 @@ inline ProgramLayout program_layout(const std::string &op, const std::vector<uin
     else if (op == "radix_shl") { l = {true, at(0), {at(1)}, at(1)}; }
     else if (op.rfind("radix_scalar_", 0) == 0) { l = {true, at(0), {at(1)}, 1}; }
     else if (op == "string_eq" || op == "string_ne" || op == "string_starts_with" || op == "string_ends_with") { l = {true, at(0), {at(1) * at(3), at(2) * at(3)}, 1}; }
-    else if (op == "string_to_uppercase" || op == "string_to_lowercase") { l = {true, at(0), {at(1) * at(2)}, at(1) * at(2)}; }
+    else if (op.rfind("string_to_uppercase", 0) == 0 || op.rfind("string_to_lowercase", 0) == 0) { l = {true, at(0), {at(1) * at(2)}, at(1) * at(2)}; }
     else if (op == "string_contains") { l = {true, at(0), {at(1) * at(3), at(2) * at(3)}, 1}; }
     else if (op == "string_find") { l = {true, at(0), {at(1) * at(3), at(2) * at(3)}, 1 + at(3)}; }
     return l;   // anything else (trivium, custom circuits): one unit, runs on the first GPU

@@ -129,8 +129,24 @@ inline Radix radix_sub(Circuit &c, Radix a, Radix b) {
     return r;
 }
 
-// unchecked_eq_parallelized, radix_parallel/comparison.rs:10-33: block `==` flags (one bivariate PBS each), then all-true
+// unchecked_eq_parallelized, radix_parallel/comparison.rs:10-33: block `==` flags, then all-true.  The reference spends one
+// bivariate lookup per block; with carry_modulus >= message_modulus the flags are formed here per PAIR of blocks with the
+// packing of the reference's own comparator (pack_block_chunk + TRUE LWE subtraction, comparator.rs:191-220,430-443): the
+// difference of two packed blocks lies in (-modulus_sup, modulus_sup), and the table (x == 0) needs no sign fix-up because it
+// is 0 on every non-zero entry, so the negacyclic half (-LUT) reads -0.  Same flags, half the bootstraps; the noise of the
+// operand is that of the reference's `gt` / `lt` (two packed blocks).
 inline void radix_eq_flags(Circuit &c, const Radix &a, const Radix &b, std::vector<Lin> &out) {
+    if (a.size() != b.size()) throw std::invalid_argument("radix_eq_flags: block counts differ");
+    if (c.carry_mod >= c.msg_mod) {
+        const int lut = c.lut([](uint64_t x) { return (uint64_t)(x == 0); });
+        for (size_t i = 0; i < a.size(); i += 2) {
+            const bool pair = i + 1 < a.size();
+            const Lin pa = pair ? c.axpy(a[i + 1], c.msg_mod, a[i], 1) : a[i];
+            const Lin pb = pair ? c.axpy(b[i + 1], c.msg_mod, b[i], 1) : b[i];
+            out.push_back(c.pbs_unchecked(c.sub(pa, pb), lut, 1));   // deliberately through the padding bit
+        }
+        return;
+    }
     const int lut = c.lut_bivariate([](uint64_t x, uint64_t y) { return (uint64_t)(x == y); }, c.msg_mod);
     for (size_t i = 0; i < a.size(); i++) out.push_back(c.pbs_bivariate(a[i], b[i], lut, c.msg_mod));
 }
@@ -139,14 +155,9 @@ inline Lin radix_eq(Circuit &c, const Radix &a, const Radix &b) {
     radix_eq_flags(c, a, b, cmp);
     return all_true(c, cmp);
 }
+// ne_parallelized: radix_parallel/comparison.rs:39-62 (block `!=` flags, then any-true) = the leveled negation of eq
+inline Lin radix_ne(Circuit &c, const Radix &a, const Radix &b) { return bool_not(c, radix_eq(c, a, b)); }
 
-// ne_parallelized: radix_parallel/comparison.rs:39-62 (block `!=` flags, then any-true)
-inline Lin radix_ne(Circuit &c, const Radix &a, const Radix &b) {
-    const int lut = c.lut_bivariate([](uint64_t x, uint64_t y) { return (uint64_t)(x != y); }, c.msg_mod);
-    std::vector<Lin> cmp(a.size());
-    for (size_t i = 0; i < a.size(); i++) cmp[i] = c.pbs_bivariate(a[i], b[i], lut, c.msg_mod);
-    return any_true(c, cmp);
-}
 // bitand / bitor / bitxor_parallelized (integer/server_key/radix_parallel/bitwise_op.rs -> per block
 // shortint unchecked_bitand/bitor/bitxor, shortint/server_key/bitwise_op.rs:204-207): one bivariate PBS per block
 inline Radix radix_bitop(Circuit &c, const Radix &a, const Radix &b, char op) {
@@ -325,18 +336,43 @@ inline Radix bool_to_radix(Circuit &c, const Lin &b, size_t n_blocks) {   // exa
 // ---- FheString operations (examples/fhe_strings/server_key/*)
 using FheChars = std::vector<Radix>;   // one radix (4 blocks) per character, no padding, clear length
 
-// to_uppercase_char, change_case.rs:53-67: (c > 96 & c < 123) -> c - 32 * flag
-inline Radix to_uppercase_char(Circuit &c, const Radix &ch) {
+// to_uppercase_char, change_case.rs:53-67: (c > 96 & c < 123) -> c - 32 * flag; the reference's own decomposition
+// (two scalar comparisons, a boolean and, a shift and a subtraction with carry propagation: 18 bootstraps, depth 7)
+inline Radix to_uppercase_char_reference(Circuit &c, const Radix &ch) {
     Lin flag = bool_and(c, scalar_gt(c, ch, 96), scalar_lt(c, ch, 123));
     Radix delta = scalar_left_shift(c, bool_to_radix(c, flag, ch.size()), 5);   // scalar_mul_parallelized(.., 32)
     return radix_sub(c, ch, delta);
 }
 // to_lowercase_char, change_case.rs:69-82: (c > 64 & c < 91) -> c + 32 * flag
-inline Radix to_lowercase_char(Circuit &c, const Radix &ch) {
+inline Radix to_lowercase_char_reference(Circuit &c, const Radix &ch) {
     Lin flag = bool_and(c, scalar_gt(c, ch, 64), scalar_lt(c, ch, 91));
     Radix delta = scalar_left_shift(c, bool_to_radix(c, flag, ch.size()), 5);
     return radix_add(c, ch, delta);
 }
+// The same function on an 8-bit character held in four 2-bit blocks, scheduled for the batch (3 bootstraps, depth 2).
+// With hi = packed blocks 3,2 and lo = packed blocks 1,0 (pack_block_chunk), the letters to change are hi = h0 with
+// lo >= 1 or hi = h0 + 1 with lo <= 10 (h0 = 6 for a..z, 4 for A..Z), and adding / subtracting 32 only changes block 2
+// by 2, never with a carry or a borrow (block 2 is 2 or 3 for a..z, 0 or 1 for A..Z).  So: one lookup on hi (which row),
+// one on lo (which of the two bounds hold), one on their packing (2 * flag), and a leveled +- on block 2.  Decrypted
+// results are those of the reference's decomposition for all 256 byte values (tests); the other three blocks are the inputs.
+inline Radix case_change_char(Circuit &c, const Radix &ch, bool to_upper) {
+    if (!(c.msg_mod == 4 && c.carry_mod >= 4 && ch.size() == 4))
+        return to_upper ? to_uppercase_char_reference(c, ch) : to_lowercase_char_reference(c, ch);
+    const uint64_t h0 = to_upper ? 6 : 4;
+    const Lin hi = c.axpy(ch[3], 4, ch[2], 1), lo = c.axpy(ch[1], 4, ch[0], 1);
+    const Lin row = c.pbs(hi, c.lut([h0](uint64_t x) { return x == h0 ? (uint64_t)1 : x == h0 + 1 ? (uint64_t)2 : (uint64_t)0; }));
+    const Lin bounds = c.pbs(lo, c.lut([](uint64_t x) { return (uint64_t)(x >= 1) + 2 * (uint64_t)(x <= 10); }));
+    const Lin twice_flag = c.pbs(c.axpy(row, 4, bounds, 1), c.lut([](uint64_t x) {
+        const uint64_t r = x / 4, b = x % 4;
+        return (uint64_t)(((r == 1 && (b & 1)) || (r == 2 && (b & 2))) ? 2 : 0);
+    }));
+    Radix out = ch;
+    out[2] = to_upper ? c.sub(ch[2], twice_flag) : c.add(ch[2], twice_flag);
+    out[2].degree = c.msg_mod - 1;   // the value stays a clean 2-bit block (no borrow / carry by construction)
+    return out;
+}
+inline Radix to_uppercase_char(Circuit &c, const Radix &ch) { return case_change_char(c, ch, true); }
+inline Radix to_lowercase_char(Circuit &c, const Radix &ch) { return case_change_char(c, ch, false); }
 // eq_no_init_padding for two unpadded strings (comparisons.rs:184-215); the serial `&=` fold of the
 // reference becomes one sum-of-flags tree over all character comparisons
 inline Lin string_eq(Circuit &c, const FheChars &a, const FheChars &b) {
