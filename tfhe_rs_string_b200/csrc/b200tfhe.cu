@@ -255,19 +255,47 @@ int launch_ks(b200tfhe_ctx *ctx, DevCtx &d, const uint64_t *d_in, uint64_t *d_ou
     return 0;
 }
 
-// Ciphertexts per CTA of the specialised kernels: the fewest that still fit the batch into the minimum number of
-// waves over the SMs (one CTA per SM).  Large batches get 4 (throughput); a dependency level with few bootstraps
-// gets the latency kernel (1 or 2 per SM, two warps per polynomial) or 3, which shortens every CMUX step.
-void launch_pbs_fast(DevCtx &d, const PbsArgs &a) {
-    const long long sms = d.sm_count;
-    const long long waves = (a.batch + 4LL * sms - 1) / (4LL * sms);
-    const long long per_cta = (a.batch + waves * sms - 1) / (waves * sms);
-    switch ((int)per_cta) {
+// Ciphertexts per CTA of the specialised kernels (one CTA per SM).  One launch with c ciphertexts per CTA takes a whole
+// number of waves of t(c) each; measured on this pool's B200 per wave: 4.2 ms for 1 per SM (latency kernel: two warps per
+// polynomial), 4.75 ms for 2, 6.5 ms for 3 and 6.9 ms for 4 (pbs_kernel5).  A batch is served either by ONE launch with the
+// fewest ciphertexts per CTA that still fits it into the minimum number of waves, or by a launch of full 4-per-SM waves
+// followed by a second launch for the remainder with the kernel that suits the remainder (700 = 592 + 108: 6.9 + 4.2 ms
+// instead of two waves of 3 per SM = 13 ms) -- whichever the wave model says is shorter.
+struct PbsWaveModel { double t1 = 4.2, t2 = 4.75, t3 = 6.5, t4 = 6.9, split_penalty = 0.15; };
+inline int pbs_per_cta(long long batch, long long sms) {
+    const long long waves = (batch + 4 * sms - 1) / (4 * sms);
+    return (int)((batch + waves * sms - 1) / (waves * sms));
+}
+void launch_pbs_one(DevCtx &d, const PbsArgs &a, int per_cta) {
+    switch (per_cta) {
         case 1: pbs_lat_kernel<1><<<(unsigned)a.batch, 256, pbs_lat_smem_bytes<1>(), d.stream>>>(a); break;
         case 2: pbs_lat_kernel<2><<<(unsigned)((a.batch + 1) / 2), 256, pbs_lat_smem_bytes<2>(), d.stream>>>(a); break;
         case 3: pbs_kernel5<3><<<(unsigned)((a.batch + 2) / 3), 192, pbs5_smem_bytes<3>(), d.stream>>>(a); break;
         default: pbs_kernel5<4><<<(unsigned)((a.batch + 3) / 4), 256, pbs5_smem_bytes<4>(), d.stream>>>(a); break;
     }
+}
+void launch_pbs_fast(DevCtx &d, const PbsArgs &a) {
+    const PbsWaveModel m;
+    const long long sms = d.sm_count, full = a.batch / (4 * sms), rest = a.batch - full * 4 * sms;
+    const double t[5] = {0, m.t1, m.t2, m.t3, m.t4};
+    const int c_one = pbs_per_cta(a.batch, sms);
+    const double one = (double)((a.batch + c_one * sms - 1) / (c_one * sms)) * t[c_one];
+    if (full > 0 && rest > 0) {
+        const int c_rest = pbs_per_cta(rest, sms);
+        if ((double)full * m.t4 + t[c_rest] + m.split_penalty < one) {
+            PbsArgs head = a, tail = a;
+            head.batch = (int)(full * 4 * sms);
+            tail.batch = (int)rest;
+            tail.lwe_small = a.lwe_small + (size_t)head.batch * (a.n + 1);
+            tail.lut_idx = a.lut_idx ? a.lut_idx + head.batch : nullptr;
+            tail.out = a.out + (size_t)head.batch * (kN + 1);
+            launch_pbs_one(d, head, 4);
+            launch_pbs_one(d, tail, c_rest);
+            d.kernel_launches++;   // (the caller counts one)
+            return;
+        }
+    }
+    launch_pbs_one(d, a, c_one);
 }
 
 int launch_pbs(b200tfhe_ctx *ctx, DevCtx &d, const uint64_t *d_small, const uint32_t *d_lut_idx, uint64_t *d_out, size_t batch) {
