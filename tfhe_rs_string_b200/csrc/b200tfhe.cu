@@ -100,7 +100,7 @@ int configure_device_once(int device) {
     };
     set((const void *)pbs_kernel5<3>, (int)pbs5_smem_bytes<3>());
     set((const void *)pbs_kernel5<4>, (int)pbs5_smem_bytes<4>());
-    set((const void *)pbs_lat_kernel<1>, (int)pbs_lat_smem_bytes<1>());
+    set((const void *)pbs_lat_kernel<1, true>, (int)pbs_lat_smem_bytes<1, true>());
     set((const void *)pbs_lat_kernel<2>, (int)pbs_lat_smem_bytes<2>());
     // parameter-independent maxima: two live contexts with different keyswitch levels share these functions
     set((const void *)ks_mma_kernel, kMaxOptinSmem);
@@ -268,7 +268,7 @@ inline int pbs_per_cta(long long batch, long long sms) {
 }
 void launch_pbs_one(DevCtx &d, const PbsArgs &a, int per_cta) {
     switch (per_cta) {
-        case 1: pbs_lat_kernel<1><<<(unsigned)a.batch, 256, pbs_lat_smem_bytes<1>(), d.stream>>>(a); break;
+        case 1: pbs_lat_kernel<1, true><<<(unsigned)a.batch, 128, pbs_lat_smem_bytes<1, true>(), d.stream>>>(a); break;
         case 2: pbs_lat_kernel<2><<<(unsigned)((a.batch + 1) / 2), 256, pbs_lat_smem_bytes<2>(), d.stream>>>(a); break;
         case 3: pbs_kernel5<3><<<(unsigned)((a.batch + 2) / 3), 192, pbs5_smem_bytes<3>(), d.stream>>>(a); break;
         default: pbs_kernel5<4><<<(unsigned)((a.batch + 3) / 4), 256, pbs5_smem_bytes<4>(), d.stream>>>(a); break;

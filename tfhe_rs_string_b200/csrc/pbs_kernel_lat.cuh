@@ -104,30 +104,40 @@ __device__ __forceinline__ void lat_get8(double (&vr)[16], double (&vi)[16], con
         vr[off + 4 + j] = dbl(g1[4 * j], g1[4 * j + 1]); vi[off + 4 + j] = dbl(g1[4 * j + 2], g1[4 * j + 3]);
     }
 }
-// swap 16 complex values with the sibling warp: send v, receive r
-template <bool TWO_ROUNDS>
+// swap 16 complex values with the sibling warp: send v, receive r.  MODE 0: one round through TMEM (siblings share a TMEM
+// quadrant), 1: two rounds through TMEM (16-warp configuration), 2: through shared memory (siblings on different SM
+// sub-partitions, see kSpread below; sx_own / sx_oth alternate between two buffers from call to call, so that a buffer is
+// rewritten only after the pair barrier of the following swap).
+template <int MODE>
 __device__ __forceinline__ void lat_swap(const double (&vr)[16], const double (&vi)[16], double (&rr)[16], double (&ri)[16],
-                                         const uint32_t xout, const uint32_t xin, const int bar) {
-    if (!TWO_ROUNDS) {
+                                         const uint32_t xout, const uint32_t xin, double2 *sx_own, const double2 *sx_oth, const int bar) {
+    if (MODE == 0) {
         lat_send(vr, vi, xout);
         pair_barrier(bar);
         lat_recv(rr, ri, xin);
-    } else {
+    } else if (MODE == 1) {
         lat_put8(vr, vi, 0, xout);
         pair_barrier(bar);
         lat_get8(rr, ri, 0, xin);
         lat_put8(vr, vi, 8, xin);     // the buffer just read; the sibling fills xout
         pair_barrier(bar);
         lat_get8(rr, ri, 8, xout);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) sx_own[k * 32] = make_double2(vr[k], vi[k]);
+        pair_barrier(bar);
+#pragma unroll
+        for (int k = 0; k < 16; k++) { const double2 v = sx_oth[k * 32]; rr[k] = v.x; ri[k] = v.y; }
     }
 }
 
 // forward cross-warp stage + 16-point transform: x natural (own half) -> y[kappa] = output 2 kappa + h
-template <bool TWO_ROUNDS>
+template <int MODE>
 __device__ __forceinline__ void lat_fwd_pass(const double (&xr)[16], const double (&xi)[16], double (&yr)[16], double (&yi)[16],
-                                             const int h, const double sgn, const uint32_t xout, const uint32_t xin, const int bar) {
+                                             const int h, const double sgn, const uint32_t xout, const uint32_t xin,
+                                             double2 *sx_own, const double2 *sx_oth, const int bar) {
     double rr[16], ri[16];
-    lat_swap<TWO_ROUNDS>(xr, xi, rr, ri, xout, xin, bar);
+    lat_swap<MODE>(xr, xi, rr, ri, xout, xin, sx_own, sx_oth, bar);
 #pragma unroll
     for (int mm = 0; mm < 16; mm++) {
         double tr = fma(sgn, rr[mm], xr[mm]), ti = fma(sgn, ri[mm], xi[mm]);
@@ -144,9 +154,10 @@ __device__ __forceinline__ void lat_fwd_pass(const double (&xr)[16], const doubl
     fft16_dit<false>(yr, yi);
 }
 // inverse: x[brev4(kappa)] = inputs 2 kappa + h -> y[mm] = result for index mm + 16 h
-template <bool TWO_ROUNDS>
+template <int MODE>
 __device__ __forceinline__ void lat_inv_pass(double (&xr)[16], double (&xi)[16], double (&yr)[16], double (&yi)[16],
-                                             const int h, const double sgn, const uint32_t xout, const uint32_t xin, const int bar) {
+                                             const int h, const double sgn, const uint32_t xout, const uint32_t xin,
+                                             double2 *sx_own, const double2 *sx_oth, const int bar) {
     fft16_dit<true>(xr, xi);
     if (h) {
 #pragma unroll
@@ -157,7 +168,7 @@ __device__ __forceinline__ void lat_inv_pass(double (&xr)[16], double (&xi)[16],
             xr[mm] = nr;
         }
     }
-    lat_swap<TWO_ROUNDS>(xr, xi, yr, yi, xout, xin, bar);
+    lat_swap<MODE>(xr, xi, yr, yi, xout, xin, sx_own, sx_oth, bar);
 #pragma unroll
     for (int mm = 0; mm < 16; mm++) {
         yr[mm] = fma(sgn, xr[mm], yr[mm]);
@@ -168,23 +179,30 @@ __device__ __forceinline__ void lat_inv_pass(double (&xr)[16], double (&xi)[16],
 // per ciphertext: two polynomial buffers (rotation copy with its overflow zone / transposition / transform, see
 // pbs_kernel5.cuh) and the a~ table
 __host__ __device__ constexpr size_t pbs_lat_ct_bytes() { return (size_t)2 * kBuf5Bytes + kMaxSmallDim * sizeof(uint16_t); }
-template <int CTS>
+constexpr int kLatSxBytes = 2 * 2 * 16 * 32 * (int)sizeof(double2);   // per polynomial: two buffers x two halves x 16 values x 32 lanes
+template <int CTS, bool kSpread = false>
 __host__ __device__ constexpr size_t pbs_lat_smem_bytes() {
-    return kPbsHeaderBytes + kBskSliceBytes + (size_t)CTS * pbs_lat_ct_bytes();
+    return kPbsHeaderBytes + kBskSliceBytes + (size_t)CTS * pbs_lat_ct_bytes() + (kSpread ? 2 * kLatSxBytes : 0);
 }
 
 // CTS = 1, 2: 8 warps (latency); CTS = 4: 16 warps, 128 registers per thread, two polynomial pairs per
 // TMEM quadrant (ciphertexts c and c + 2 share the sub-partitions), two-round exchanges (throughput).
-template <int CTS>
-__global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const PbsArgs a) {
+// kSpread (one ciphertext per CTA, 4 warps): the two halves of a polynomial run on DIFFERENT SM sub-partitions (warp = p + 2 h,
+// one warp per sub-partition and TMEM quadrant) and swap through shared memory.  With both halves on one sub-partition
+// (the TMEM exchange needs a common quadrant) the 2,860 FP64 instructions of a polynomial's CMUX step share one FP64 pipe
+// and two of the SM's four pipes idle; spread out, every pipe carries 1,430.
+template <int CTS, bool kSpread = false>
+__global__ void __launch_bounds__(kSpread ? 128 : CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const PbsArgs a) {
     static_assert(CTS == 1 || CTS == 2 || CTS == 4, "1, 2 or 4 ciphertexts per CTA");
+    static_assert(!kSpread || CTS == 1, "the spread mapping is for one ciphertext per CTA");
     constexpr bool kTwoRounds = CTS == 4;
+    constexpr int kX = kSpread ? 2 : kTwoRounds ? 1 : 0;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qd = warp & 3, h = (warp >> 2) & 1, pr = warp >> 3;
-    const int ctl = 2 * pr + (qd >> 1), p = qd & 1;
+    const int qd = warp & 3, h = kSpread ? (warp >> 1) : (warp >> 2) & 1, pr = kSpread ? 0 : warp >> 3;
+    const int ctl = kSpread ? 0 : 2 * pr + (qd >> 1), p = kSpread ? (warp & 1) : (qd & 1);
     const int ct = blockIdx.x * CTS + ctl;
-    const bool active = ctl < CTS && ct < a.batch;
+    const bool active = ctl < CTS && ct < a.batch;   // (kSpread: all four warps belong to the CTA's one ciphertext)
     const double sgn = h ? -1.0 : 1.0;
 
     uint32_t *slot = reinterpret_cast<uint32_t *>(smem);
@@ -211,7 +229,11 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
     const uint32_t t_acc = tquad + kLatAcc + (uint32_t)(pr * 2 + h) * 64u;
     const uint32_t t_x_own = kTwoRounds ? tquad + 384u + (uint32_t)(pr * 2 + h) * 32u : tquad + kLatX + (uint32_t)h * 64u;
     const uint32_t t_x_oth = kTwoRounds ? tquad + 384u + (uint32_t)(pr * 2 + 1 - h) * 32u : tquad + kLatX + (uint32_t)(1 - h) * 64u;
-    const int bar_pair = 1 + qd + 4 * pr, bar_ct = 9 + ctl;
+    const int bar_pair = kSpread ? 1 + p : 1 + qd + 4 * pr, bar_ct = 9 + ctl;
+    // kSpread: shared-memory swap buffers of this polynomial, [buffer b][half][16][32 lanes]
+    double2 *sx = reinterpret_cast<double2 *>(smem + kPbsHeaderBytes + kBskSliceBytes + (size_t)CTS * pbs_lat_ct_bytes() + (size_t)p * kLatSxBytes);
+    double2 *sx_own0 = sx + (0 * 2 + h) * 512 + lane, *sx_own1 = sx + (1 * 2 + h) * 512 + lane;
+    const double2 *sx_oth0 = sx + (0 * 2 + 1 - h) * 512 + lane, *sx_oth1 = sx + (1 * 2 + 1 - h) * 512 + lane;
     if (pr == 0) {   // the quadrant's inter-pass twiddles T'[2 kappa + h][lane], one table per half
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -306,7 +328,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
             PBS3_TS(1);
             // ---- forward transform
             double yr[16], yi[16];
-            lat_fwd_pass<kTwoRounds>(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);
+            lat_fwd_pass<kX>(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, sx_own0, sx_oth0, bar_pair);
             {
                 uint32_t t0[16], t1[16];
                 tmem_ld16_nc(t_tw, t0);
@@ -331,7 +353,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
                 const double2 v = tb_own[(ll + 16 * h) * kTStride + lane];
                 xr[ll] = v.x; xi[ll] = v.y;
             }
-            lat_fwd_pass<kTwoRounds>(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier also orders the transposition reads before the writes below
+            lat_fwd_pass<kX>(xr, xi, yr, yi, h, sgn, t_x_own, t_x_oth, sx_own1, sx_oth1, bar_pair);   // its barrier also orders the transposition reads before the writes below
 
             PBS3_TS(3);
             // ---- exchange the transforms between the two polynomials, Out_p = B[p][p] F_p + B[1-p][p] F_{1-p}
@@ -372,7 +394,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
 
             PBS3_TS(7);
             // ---- inverse transform
-            lat_inv_pass<kTwoRounds>(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // y[ll]: index l = ll + 16 h of lane k1
+            lat_inv_pass<kX>(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, sx_own0, sx_oth0, bar_pair);   // y[ll]: index l = ll + 16 h of lane k1
 #pragma unroll
             for (int ll = 0; ll < 16; ll++) tb_own[lane * kTStride + ll + 16 * h] = make_double2(yr[ll], yi[ll]);
             pair_barrier(bar_pair);
@@ -392,7 +414,7 @@ __global__ void __launch_bounds__(CTS == 4 ? 512 : 256, 1) pbs_lat_kernel(const 
                     }
                 }
             }
-            lat_inv_pass<kTwoRounds>(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, bar_pair);   // its barrier orders the transposition reads before the rotation copy below
+            lat_inv_pass<kX>(zr, zi, yr, yi, h, sgn, t_x_own, t_x_oth, sx_own1, sx_oth1, bar_pair);   // its barrier orders the transposition reads before the rotation copy below
 
             PBS3_TS(8);
             // ---- phase D: untwist, from_torus, G -= delta, refresh both copies

@@ -43,11 +43,11 @@ static void launch5(const PbsArgs &a, cudaStream_t s) {
     pbs_kernel5<CTS, PH><<<(a.batch + CTS - 1) / CTS, CTS * 64, smem, s>>>(a);
 }
 
-template <int CTS>
+template <int CTS, bool SPREAD = false>
 static void launch_lat(const PbsArgs &a, cudaStream_t s) {
-    constexpr size_t smem = pbs_lat_smem_bytes<CTS>();
-    CK(cudaFuncSetAttribute(pbs_lat_kernel<CTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pbs_lat_kernel<CTS><<<(a.batch + CTS - 1) / CTS, 256, smem, s>>>(a);
+    constexpr size_t smem = pbs_lat_smem_bytes<CTS, SPREAD>();
+    CK(cudaFuncSetAttribute(pbs_lat_kernel<CTS, SPREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pbs_lat_kernel<CTS, SPREAD><<<(a.batch + CTS - 1) / CTS, SPREAD ? 128 : 256, smem, s>>>(a);
 }
 
 int main(int argc, char **argv) {
@@ -82,6 +82,7 @@ int main(int argc, char **argv) {
         if (kernel == 31) launch3<4, 1>(x, 0);
         else if (kernel == 51) launch5<4, 1>(x, 0);
         else if (kernel == 7) { if (cts == 1) launch_lat<1>(x, 0); else launch_lat<2>(x, 0); }
+        else if (kernel == 72) launch_lat<1, true>(x, 0);   // one ciphertext per SM, the halves of a polynomial on different sub-partitions
         else if (kernel == 5) {
             switch (cts) { case 1: launch5<1>(x, 0); break; case 2: launch5<2>(x, 0); break; case 3: launch5<3>(x, 0); break; default: launch5<4>(x, 0); }
         }
