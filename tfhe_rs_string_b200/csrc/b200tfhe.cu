@@ -316,9 +316,10 @@ int launch_pbs(b200tfhe_ctx *ctx, DevCtx &d, const uint64_t *d_small, const uint
         g.batch = (int)batch; g.n = (int)ctx->p.lwe_dimension; g.k = (int)ctx->p.glwe_dimension; g.log2N = ctx->log2N;
         g.base_log = (int)ctx->p.pbs_base_log; g.level = (int)ctx->p.pbs_level; g.fft_in_smem = ctx->fft_in_smem ? 1 : 0;
         g.n_luts = (uint32_t)d.lut_count; g.err_flag = d.d_err_flag;
-        const size_t smem = ctx->fft_in_smem ? (size_t)ctx->p.polynomial_size * 3 / 4 * sizeof(double2) : 0;   // buffer + roots
-        // one butterfly per thread and stage for small polynomials: a block barrier over 4 warps costs a third of one over 16
-        const unsigned threads = std::min(1024u, std::max(128u, ctx->p.polynomial_size / 4));
+        const GenLaunch gl = gen_launch_shape(ctx->p.polynomial_size, ctx->p.glwe_dimension, ctx->p.pbs_level, ctx->fft_in_smem, kMaxOptinSmem);
+        g.polys_in_smem = gl.polys_in_smem;
+        const size_t smem = gl.smem;
+        const unsigned threads = gl.threads;
         pbs_generic_kernel<uint64_t><<<(unsigned)batch, threads, smem, d.stream>>>(g);
     }
     prof_end(d, d.ev_pbs);

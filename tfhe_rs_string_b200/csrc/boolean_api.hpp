@@ -185,9 +185,11 @@ int b200tfhe_boolean_gate_batch(b200tfhe_boolean_ctx *ctx, int gate, const uint3
     g.lut_idx = nullptr; g.luts = ctx->d_lut; g.bsk = ctx->d_bsk; g.roots = ctx->d_roots; g.twist = ctx->d_twist;
     g.acc_ws = ctx->d_acc; g.fourier_ws = ctx->d_fourier; g.batch = (int)batch; g.n = (int)p.lwe_dimension; g.k = (int)p.glwe_dimension;
     g.log2N = ctx->log2N; g.base_log = (int)p.pbs_base_log; g.level = (int)p.pbs_level; g.fft_in_smem = 1; g.n_luts = 1; g.err_flag = nullptr;
-    const size_t smem = (size_t)p.polynomial_size * 3 / 4 * sizeof(double2);   // FFT buffer + roots of unity
+    const GenLaunch gl = gen_launch_shape(p.polynomial_size, p.glwe_dimension, p.pbs_level, true, kMaxOptinSmem);
+    g.polys_in_smem = gl.polys_in_smem;
+    const size_t smem = gl.smem;   // FFT buffers + roots of unity
     const int n_in = (int)(p.glwe_dimension * p.polynomial_size);
-    const unsigned threads = std::min(512u, std::max(128u, p.polynomial_size / 4));
+    const unsigned threads = gl.threads;
     if (ctx->ks_first) {
         ks_generic_kernel<uint32_t><<<(unsigned)batch, 256, 0, ctx->stream>>>(ctx->d_mid, ctx->d_ksk, ctx->d_mid2, (int)batch, n_in, (int)ctx->small(),
                                                                                (int)p.ks_base_log, (int)p.ks_level);

@@ -83,6 +83,32 @@ __device__ __forceinline__ void fft32_dit(double (&xr)[32], double (&xi)[32]) {
     }
 }
 
+// The forward first pass with the register part C_m of the twist folded in: X_k = sum_m d_m C_m W32^(m k) is a DFT shifted
+// by -1/4 of a frequency bin, and the decimation-in-time recursion keeps the shift at every size, so the butterfly t of
+// the stage with distance `half` uses exp(-2 pi i (t - 1/4) / (2 half)) (c_w32s[(half - 1) + t]) and the inputs are the
+// untwisted points.  80 generic butterflies = 480 FP64 instructions against 124 (twist) + 388.
+__device__ __constant__ double2 c_w32s[32] = {B200_W32_SHIFTED_TABLE};
+__device__ __forceinline__ void fft32_dit_twisted(double (&xr)[32], double (&xi)[32]) {
+#pragma unroll
+    for (int half = 1; half < 32; half <<= 1) {
+#pragma unroll
+        for (int base = 0; base < 32; base += 2 * half) {
+#pragma unroll
+            for (int t = 0; t < half; t++) {
+                const double wr = c_w32s[half - 1 + t].x, wi = c_w32s[half - 1 + t].y;
+                double &ar = xr[base + t], &ai = xi[base + t], &br = xr[base + t + half], &bi = xi[base + t + half];
+                double sr = fma(wr, br, ar);
+                sr = fma(-wi, bi, sr);
+                double si = fma(wr, bi, ai);
+                si = fma(wi, br, si);
+                br = fma(2.0, ar, -sr);
+                bi = fma(2.0, ai, -si);
+                ar = sr; ai = si;
+            }
+        }
+    }
+}
+
 // Twiddle sources: T'[k1][lane] for k1 = 4*chunk .. 4*chunk+3, as 16 32-bit words
 // (re.lo, re.hi, im.lo, im.hi per twiddle).  issue() may be asynchronous; wait() completes it.
 struct GlobalTwiddles {   // plain global-memory table (key conversion / unit-test kernels)

@@ -42,14 +42,19 @@ __device__ __forceinline__ uint64_t from_torus_dev(double x) {
 
 __device__ __forceinline__ uint64_t pack64(const uint32_t lo, const uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 constexpr uint64_t kFtBias = 0x4338000000000000ull;           // bit pattern of 1.5 * 2^52
-// from_torus on the FP64 pipe only.  |x| < 2^37.  Returns d with  round_half_even(x * 2^64) mod 2^64 = d - kFtBias.
-//   t = x + 1.5*2^38 has ulp 2^-14: its low mantissa word holds round(x * 2^14);  l = x - (t - 1.5*2^38) is exact,
-//   |l| <= 2^-15;  u = l * 2^64 + 1.5*2^52 holds round_half_even(l * 2^64) as a 52-bit two's complement mantissa.
+// from_torus on the FP64 pipe only, three instructions.  |x| < 2^37.  Returns d with
+// round_half_even(x * 2^64) mod 2^64 = d - kFtBias.
+//   u1 = x * 2^64 + 1.5*2^102 has ulp 2^50: its low mantissa word holds T = round(x * 2^14) (two's complement);
+//   c = (1.5*2^102 + 1.5*2^52) - u1 = 1.5*2^52 - T * 2^50 is exact (a multiple of 2^50 below 2^103);
+//   u = x * 2^64 + c is ONE rounding of x * 2^64 - T * 2^50 + 1.5*2^52 (|x * 2^64 - T * 2^50| <= 2^49), i.e. it holds
+//   round_half_even(x * 2^64) - T * 2^50 as a 52-bit two's complement mantissa.
+// (Round 2 started with the four-instruction form t = x + 1.5*2^38, l = x - (t - 1.5*2^38), u = l * 2^64 + 1.5*2^52: the
+// same T and the same u, one more dependent FP64 instruction per coefficient.)
 __device__ __forceinline__ uint64_t from_torus_fp(const double x) {
-    const double t = x + 412316860416.0;                       // 1.5 * 2^38
-    const double l = x - (t - 412316860416.0);
-    const double u = fma(l, 18446744073709551616.0, 6755399441055744.0);
-    return pack64((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u) + ((uint32_t)__double2loint(t) << 18));
+    const double u1 = fma(x, 18446744073709551616.0, __longlong_as_double(0x4658000000000000ll));   // 1.5 * 2^102
+    const double c = __longlong_as_double(0x4658000000000006ll) - u1;                               // 1.5 * 2^102 + 1.5 * 2^52
+    const double u = fma(x, 18446744073709551616.0, c);
+    return pack64((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u) + ((uint32_t)__double2loint(u1) << 18));
 }
 // lut id of ciphertext ct; device-buffer callers cannot be validated on the host, so the range check is here
 __device__ __forceinline__ uint32_t pbs_lut_id(const PbsArgs &a, const int ct) {

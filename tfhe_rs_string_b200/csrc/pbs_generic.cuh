@@ -12,7 +12,9 @@
 //       acc_c += from_torus(IFFT(Out_c))
 // then sample extraction.  The accumulator and the k+1 Fourier accumulators live in a per-ciphertext global
 // workspace (L2 resident); the FFT runs in shared memory when N/2 complex doubles fit (N <= 16384), else in the
-// workspace.  Transform: in-place radix-2, forward decimation in frequency (natural in, bit-reversed out), inverse
+// workspace.  As many of the (k+1) * level forward transforms of a CMUX step as fit in shared memory run side by side (one
+// block barrier per butterfly stage serves all of them; the k+1 inverse transforms likewise): a single bootstrap is bound
+// by the number of block barriers per step, not by arithmetic.  Transform: in-place radix-2, forward decimation in frequency (natural in, bit-reversed out), inverse
 // decimation in time; the Fourier key is produced by the same forward transform (bsk_to_fourier_generic_kernel),
 // so the frequency order is private to this file, and pre-scaled by 2/N.
 #pragma once
@@ -33,9 +35,29 @@ struct GenPbsArgs {
     void *out;                 // [batch][k N + 1]
     int batch, n, k, log2N, base_log, level;
     int fft_in_smem;
+    int polys_in_smem;         // FFT buffers (N / 2 complex doubles each) the launch reserved in shared memory, >= 1 when fft_in_smem
     uint32_t n_luts;           // ids >= n_luts are rejected in the kernel (table 0 used, *err_flag set)
     uint32_t *err_flag;
 };
+
+// Launch shape of pbs_generic_kernel: as many FFT buffers as the (k+1) * level forward transforms of a step can use and
+// shared memory holds (next to the N/4 roots of unity), one butterfly per thread and stage of a group up to 1024 threads
+// (a block barrier over 4 warps costs a third of one over 16, so small shapes stay small).
+struct GenLaunch { int polys_in_smem; size_t smem; unsigned threads; };
+inline GenLaunch gen_launch_shape(const uint32_t N, const uint32_t k, const uint32_t level, const bool fft_in_smem, const size_t smem_limit) {
+    GenLaunch gl{1, 0, 0};
+    const uint32_t jobs = (k + 1) * level;
+    if (fft_in_smem) {
+        const size_t roots = (size_t)(N / 4) * sizeof(double2), per = (size_t)(N / 2) * sizeof(double2);
+        const size_t fit = (smem_limit - 1024 - roots) / per;
+        gl.polys_in_smem = (int)(fit < 1 ? 1 : fit > jobs ? jobs : fit);
+        gl.smem = roots + (size_t)gl.polys_in_smem * per;
+    }
+    const uint32_t rounds = (jobs + gl.polys_in_smem - 1) / gl.polys_in_smem, grp = (jobs + rounds - 1) / rounds;
+    const uint32_t want = grp * (N / 4);
+    gl.threads = want < 128u ? 128u : want > 1024u ? 1024u : want;
+    return gl;
+}
 
 template <typename Torus> struct TorusTraits;
 template <> struct TorusTraits<uint64_t> { static constexpr int bits = 64; typedef int64_t Signed; };
@@ -74,11 +96,12 @@ __device__ __forceinline__ double2 gen_cmul(const double2 a, const double2 b) {
     return make_double2(fma(-a.y, b.y, a.x * b.x), fma(a.y, b.x, a.x * b.y));
 }
 
-// in-place transforms over `buf` (n = N/2 complex points), all threads of the CTA cooperate
-__device__ __forceinline__ void gen_fft_forward(double2 *buf, const double2 *__restrict__ roots, const int n) {
+// in-place transforms over `cnt` contiguous buffers of n = N/2 complex points each, all threads of the CTA cooperate
+// (butterfly b of the concatenated array belongs to transform b / (n/2): the index arithmetic below needs no change)
+__device__ __forceinline__ void gen_fft_forward(double2 *buf, const double2 *__restrict__ roots, const int n, const int cnt = 1) {
     for (int half = n >> 1, stride = 1; half >= 1; half >>= 1, stride <<= 1) {
         __syncthreads();
-        for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+        for (int b = threadIdx.x; b < cnt * (n >> 1); b += blockDim.x) {
             const int t = b & (half - 1), base = (b - t) << 1;
             const double2 x = buf[base + t], y = buf[base + t + half];
             const double2 w = roots[t * stride];
@@ -88,10 +111,10 @@ __device__ __forceinline__ void gen_fft_forward(double2 *buf, const double2 *__r
     }
     __syncthreads();
 }
-__device__ __forceinline__ void gen_fft_inverse(double2 *buf, const double2 *__restrict__ roots, const int n) {
+__device__ __forceinline__ void gen_fft_inverse(double2 *buf, const double2 *__restrict__ roots, const int n, const int cnt = 1) {
     for (int half = 1, stride = n >> 1; half < n; half <<= 1, stride >>= 1) {
         __syncthreads();
-        for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+        for (int b = threadIdx.x; b < cnt * (n >> 1); b += blockDim.x) {
             const int t = b & (half - 1), base = (b - t) << 1;
             const double2 w = roots[t * stride];
             const double2 x = buf[base + t], y = gen_cmul(buf[base + t + half], make_double2(w.x, -w.y));
@@ -132,7 +155,7 @@ __global__ void __launch_bounds__(1024, 1) pbs_generic_kernel(const GenPbsArgs a
     // memory (a strided global load per butterfly was most of the time of a CMUX step for N = 8192)
     const double2 *roots = a.roots;
     if (a.fft_in_smem) {
-        double2 *rs = reinterpret_cast<double2 *>(gen_smem) + half;
+        double2 *rs = reinterpret_cast<double2 *>(gen_smem) + (size_t)max(1, a.polys_in_smem) * half;
         for (int t = threadIdx.x; t < (N >> 2); t += blockDim.x) rs[t] = a.roots[t];
         roots = rs;
         __syncthreads();
@@ -144,47 +167,56 @@ __global__ void __launch_bounds__(1024, 1) pbs_generic_kernel(const GenPbsArgs a
         for (int j = threadIdx.x; j < N; j += blockDim.x) acc[(size_t)r * N + j] = gen_rot(lut + (size_t)r * N, j, 2 * N - bhat, N);
     __syncthreads();
 
+    // forward transforms run in groups of `grp` (r, level) pairs, inverse transforms in groups of `grp_inv` polynomials
+    const int jobs = k1 * a.level, slots = a.fft_in_smem ? max(1, a.polys_in_smem) : 1;
+    const int grp = (jobs + (jobs + slots - 1) / slots - 1) / ((jobs + slots - 1) / slots);
+    const int grp_inv = (k1 + (k1 + slots - 1) / slots - 1) / ((k1 + slots - 1) / slots);
+    const int log2half = a.log2N - 1;
+
     for (int i = 0; i < a.n; i++) {
         const Torus ai = lwe[i];
         if (ai == 0) continue;                                           // bootstrap.rs:281
         const int ahat = (int)((((ai >> ms_shift) + 1) >> 1));
         bool first = true;
-        for (int r = 0; r < k1; r++) {
-            const Torus *ar = acc + (size_t)r * N;
-            for (int lvl = a.level; lvl >= 1; lvl--) {                   // ggsw.rs:524 (levels reversed)
-                for (int j = threadIdx.x; j < half; j += blockDim.x) {
-                    const Torus v0 = gen_rot(ar, j, ahat, N) - ar[j];
-                    const Torus v1 = gen_rot(ar, j + half, ahat, N) - ar[j + half];
-                    const double d0 = gen_digit<Torus>(v0, a.base_log, a.level, lvl);
-                    const double d1 = gen_digit<Torus>(v1, a.base_log, a.level, lvl);
-                    buf[j] = gen_cmul(make_double2(d0, d1), a.twist[j]);
-                }
-                gen_fft_forward(buf, roots, half);
-                const double2 *bk = a.bsk + ((((size_t)i * a.level + (lvl - 1)) * k1 + r) * k1) * half;
-                for (int c = 0; c < k1; c++) {
-                    const double2 *b = bk + (size_t)c * half;
-                    double2 *o = outf + (size_t)c * half;
-                    if (first) {                                         // is_output_uninit, ggsw.rs:652-676
-                        for (int f = threadIdx.x; f < half; f += blockDim.x) o[f] = gen_cmul(b[f], buf[f]);
-                    } else {
-                        for (int f = threadIdx.x; f < half; f += blockDim.x) {
-                            const double2 p = gen_cmul(b[f], buf[f]), q = o[f];
-                            o[f] = make_double2(q.x + p.x, q.y + p.y);
-                        }
-                    }
-                }
-                first = false;
-                __syncthreads();
+        // job = r * level + (level - lvl): polynomial r outermost, levels from `level` down to 1 (ggsw.rs:524), the order
+        // in which the reference adds the products into the Fourier accumulators
+        for (int j0 = 0; j0 < jobs; j0 += grp) {
+            const int cnt = min(grp, jobs - j0);
+            for (int x = threadIdx.x; x < (cnt << log2half); x += blockDim.x) {
+                const int job = j0 + (x >> log2half), j = x & (half - 1);
+                const int r = job / a.level, lvl = a.level - job % a.level;
+                const Torus *ar = acc + (size_t)r * N;
+                const Torus v0 = gen_rot(ar, j, ahat, N) - ar[j];
+                const Torus v1 = gen_rot(ar, j + half, ahat, N) - ar[j + half];
+                const double d0 = gen_digit<Torus>(v0, a.base_log, a.level, lvl);
+                const double d1 = gen_digit<Torus>(v1, a.base_log, a.level, lvl);
+                buf[x] = gen_cmul(make_double2(d0, d1), a.twist[j]);
             }
+            gen_fft_forward(buf, roots, half, cnt);
+            for (int x = threadIdx.x; x < (k1 << log2half); x += blockDim.x) {
+                const int c = x >> log2half, f = x & (half - 1);
+                double2 sum = first ? make_double2(0.0, 0.0) : outf[x];
+                for (int g = 0; g < cnt; g++) {
+                    const int job = j0 + g, r = job / a.level, lvl = a.level - job % a.level;
+                    const double2 *b = a.bsk + (((((size_t)i * a.level + (lvl - 1)) * k1 + r) * k1) + c) * half;
+                    const double2 p = gen_cmul(b[f], buf[((size_t)g << log2half) + f]);
+                    sum = (first && g == 0) ? p : make_double2(sum.x + p.x, sum.y + p.y);   // is_output_uninit, ggsw.rs:652-676
+                }
+                outf[x] = sum;
+            }
+            first = false;
+            __syncthreads();
         }
-        for (int c = 0; c < k1; c++) {
-            const double2 *o = outf + (size_t)c * half;
-            for (int f = threadIdx.x; f < half; f += blockDim.x) buf[f] = o[f];
-            gen_fft_inverse(buf, roots, half);
-            Torus *ac = acc + (size_t)c * N;
-            for (int j = threadIdx.x; j < half; j += blockDim.x) {
+        for (int c0 = 0; c0 < k1; c0 += grp_inv) {
+            const int cnt = min(grp_inv, k1 - c0);
+            const double2 *o = outf + ((size_t)c0 << log2half);
+            for (int x = threadIdx.x; x < (cnt << log2half); x += blockDim.x) buf[x] = o[x];
+            gen_fft_inverse(buf, roots, half, cnt);
+            for (int x = threadIdx.x; x < (cnt << log2half); x += blockDim.x) {
+                const int j = x & (half - 1);
+                Torus *ac = acc + (size_t)(c0 + (x >> log2half)) * N;
                 const double2 tw = a.twist[j];
-                const double2 y = gen_cmul(buf[j], make_double2(tw.x, -tw.y));
+                const double2 y = gen_cmul(buf[x], make_double2(tw.x, -tw.y));
                 ac[j] += gen_from_torus<Torus>(y.x);
                 ac[j + half] += gen_from_torus<Torus>(y.y);
             }

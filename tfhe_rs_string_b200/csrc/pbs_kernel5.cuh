@@ -40,6 +40,15 @@ __host__ __device__ constexpr size_t pbs5_smem_bytes() {
     return kHdr5Bytes + kBskSliceBytes + (size_t)kCts * (2 * kBuf5Bytes + kMaxSmallDim * sizeof(uint16_t));
 }
 
+// from_torus in three FP64 instructions instead of four (bit-identical; derivation at from_torus_fp in pbs_common.cuh)
+#ifndef PBS5_FT3
+#define PBS5_FT3 1
+#endif
+// register part C_m of the forward twist folded into the first pass (fft32_dit_twisted, fft.cuh)
+#ifndef PBS5_TWFOLD
+#define PBS5_TWFOLD 0
+#endif
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
@@ -50,10 +59,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void acc_sub_from_torus(uint32_t &glo, uint32_t &ghi, const double x) {
     // the magic constant is lowered by 0x10CE ulps (0x10CE << 18 = 0x43380000, the high word of 1.5 * 2^52), so that the
     // multiply-add below removes the bias of u together with placing t's 14 bits: -(t.lo - 0x10CE) << 18
+#if PBS5_FT3
+    // three-instruction form (from_torus_fp, pbs_common.cuh) with the same lowered constant, 64 binades up
+    const double t = fma(x, 18446744073709551616.0, __longlong_as_double(0x4657FFFFFFFFEF32ll));   // (1.5 * 2^52 - 0x10CE) * 2^50
+    const double u = fma(x, 18446744073709551616.0, __longlong_as_double(0x4657FFFFFFFFEF38ll) - t);
+#else
     const double m1 = __longlong_as_double(0x4257FFFFFFFFEF32ll);   // 1.5 * 2^38 - 0x10CE * 2^-14
     const double t = x + m1;
     const double l = x - (t - m1);
     const double u = fma(l, 18446744073709551616.0, 6755399441055744.0);
+#endif
     uint32_t hi;
     asm("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %3, %4;" : "+r"(glo), "=r"(hi) : "r"((uint32_t)__double2loint(u)), "r"(ghi), "r"((uint32_t)__double2hiint(u)));
     ghi = (uint32_t)__double2loint(t) * 0xFFFC0000u + hi;
@@ -324,7 +339,9 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                         double fi = dbl(d1, 0x43300000u) - 4503599631564799.0;
 #endif
                         PBS_DUMP(0, d0); PBS_DUMP(1, d1);
+#if !PBS5_TWFOLD
                         twist_m(fr, fi, m);
+#endif
                         xr[brev5(m)] = fr; xi[brev5(m)] = fi;
                     }
                 }
@@ -334,7 +351,11 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
             // forward transform (fft.cuh: fwd1024), with the hand-over points of the pair protocol
             {
                 uint32_t t0[16], t1[16];
+#if PBS5_TWFOLD
+                fft32_dit_twisted(xr, xi);
+#else
                 fft32_dit<false>(xr, xi);
+#endif
                 __syncwarp();  // all rotation reads done before the buffer is reused for the transposition
                 tw.issue(0, t0);
 #pragma unroll
