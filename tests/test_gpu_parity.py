@@ -63,7 +63,7 @@ def test_keyswitch_adversarial_inputs(engine, real_keys):
     assert np.array_equal(engine.keyswitch_batch(cts), real_keys.keyswitch_batch(cts))
 
 
-# batch -> kernel chosen by the launcher on a 148-SM part (b200tfhe.cu:launch_pbs_fast): 40 -> pbs_lat_kernel<1>,
+# batch -> kernel chosen by the launcher on a 148-SM part (b200tfhe.cu:launch_pbs_fast): 40 -> pbs_lat4_kernel,
 def test_from_torus_fp_pipe_is_exact(engine):
     """The bootstrap kernels' from_torus (two exponent-aligned additions + one fused multiply-add, pbs_common.cuh) against exact
     rational arithmetic: round_half_even(frac(x) * 2^64) mod 2^64 (torus/mod.rs:72-78, fft/x86.rs:864) for magnitudes 2^-80 .. 2^36,

@@ -10,6 +10,7 @@
 #include "pbs_kernel3.cuh"
 #include "../../tfhe_rs_string_b200/csrc/pbs_kernel5.cuh"
 #include "../../tfhe_rs_string_b200/csrc/pbs_kernel_lat.cuh"
+#include "../../tfhe_rs_string_b200/csrc/pbs_kernel_lat4.cuh"
 #ifdef LAB_HAVE_K4
 #include "../../tfhe_rs_string_b200/csrc/pbs_kernel4.cuh"
 #endif
@@ -82,6 +83,10 @@ int main(int argc, char **argv) {
         if (kernel == 31) launch3<4, 1>(x, 0);
         else if (kernel == 51) launch5<4, 1>(x, 0);
         else if (kernel == 7) { if (cts == 1) launch_lat<1>(x, 0); else launch_lat<2>(x, 0); }
+        else if (kernel == 74) {   // one ciphertext per SM, four warps per polynomial
+            CK(cudaFuncSetAttribute(pbs_lat4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_lat4_smem_bytes()));
+            pbs_lat4_kernel<<<x.batch, 256, pbs_lat4_smem_bytes(), 0>>>(x);
+        }
         else if (kernel == 72) launch_lat<1, true>(x, 0);   // one ciphertext per SM, the halves of a polynomial on different sub-partitions
         else if (kernel == 5) {
             switch (cts) { case 1: launch5<1>(x, 0); break; case 2: launch5<2>(x, 0); break; case 3: launch5<3>(x, 0); break; default: launch5<4>(x, 0); }
