@@ -400,7 +400,7 @@ def run_b200(args):
         achieved = B * FLOP_PER_PBS / (pbs_ms * 1e-3) / 1e12
         n_waves = -(-B // (148 * 4))
         traffic, traffic_src = None, None
-        for prof in ("r02b_final_ncu_metrics.json",):
+        for prof in ("r02c_final_ncu_metrics.json", "r02b_final_ncu_metrics.json"):
             try:   # DRAM bytes of the dominant kernel from the committed ncu --set full capture (same batch only)
                 m = json.load(open(os.path.join(ROOT, "profiles", prof)))["pbs_kernel5<4>"]
                 if m["batch"] == B:
