@@ -103,6 +103,7 @@ int configure_device_once(int device) {
     set((const void *)pbs_kernel5<4>, (int)pbs5_smem_bytes<4>());
     set((const void *)pbs_lat_kernel<2>, (int)pbs_lat_smem_bytes<2>());
     set((const void *)pbs_lat4_kernel, (int)pbs_lat4_smem_bytes());
+    set((const void *)pbs_lat4t_kernel, (int)pbs_lat4_smem_bytes());
     // parameter-independent maxima: two live contexts with different keyswitch levels share these functions
     set((const void *)ks_mma_kernel, kMaxOptinSmem);
     set((const void *)ks_digits_kernel, 64 * 1024);
@@ -274,7 +275,7 @@ void launch_pbs_one(DevCtx &d, const PbsArgs &a, int per_cta) {
         case 1: cudaFuncSetAttribute(pbs_lat_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_lat_smem_bytes<1, true>());
                 pbs_lat_kernel<1, true><<<(unsigned)a.batch, 128, pbs_lat_smem_bytes<1, true>(), d.stream>>>(a); break;
 #else
-        case 1: pbs_lat4_kernel<<<(unsigned)a.batch, 256, pbs_lat4_smem_bytes(), d.stream>>>(a); break;
+        case 1: pbs_lat4t_kernel<<<(unsigned)a.batch, 256, pbs_lat4_smem_bytes(), d.stream>>>(a); break;
 #endif
         case 2: pbs_lat_kernel<2><<<(unsigned)((a.batch + 1) / 2), 256, pbs_lat_smem_bytes<2>(), d.stream>>>(a); break;
         case 3: pbs_kernel5<3><<<(unsigned)((a.batch + 2) / 3), 192, pbs5_smem_bytes<3>(), d.stream>>>(a); break;
