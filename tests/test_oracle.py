@@ -210,3 +210,17 @@ def test_many_luts_batch(toy_keys):
     dec = ks.decrypt_batch(out)
     exp = [[m % 4, m // 4, int(m == 5)][i] for m, i in zip(msgs, idx)]
     assert list(dec) == exp
+
+
+def test_lat4_fft_data_flow_model():
+    """The data flow of pbs_lat4_kernel (four warps per polynomial: two cross-warp radix-2 levels + 8-point transforms,
+    tools/proto_fft8x4.py) reproduces the negacyclic FFT-1024 in the frequency layout of fft.cuh, and its inverse is the inverse."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "proto_fft8x4.py")
+    spec = importlib.util.spec_from_file_location("proto_fft8x4", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fwd_err, rt_err = mod.run(seed=3)
+    assert fwd_err < 1e-12
+    assert rt_err < 1e-6     # values up to 2^22, unnormalised transforms of 1024 points

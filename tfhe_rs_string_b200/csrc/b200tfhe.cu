@@ -103,7 +103,6 @@ int configure_device_once(int device) {
     set((const void *)pbs_kernel5<4>, (int)pbs5_smem_bytes<4>());
     set((const void *)pbs_lat_kernel<2>, (int)pbs_lat_smem_bytes<2>());
     set((const void *)pbs_lat4_kernel, (int)pbs_lat4_smem_bytes());
-    set((const void *)pbs_lat4t_kernel, (int)pbs_lat4_smem_bytes());
     // parameter-independent maxima: two live contexts with different keyswitch levels share these functions
     set((const void *)ks_mma_kernel, kMaxOptinSmem);
     set((const void *)ks_digits_kernel, 64 * 1024);
@@ -258,13 +257,13 @@ int launch_ks(b200tfhe_ctx *ctx, DevCtx &d, const uint64_t *d_in, uint64_t *d_ou
 }
 
 // Ciphertexts per CTA of the specialised kernels (one CTA per SM).  One launch with c ciphertexts per CTA takes a whole
-// number of waves of t(c) each; measured on this pool's B200 per wave: 3.7 ms for 1 per SM (pbs_lat4_kernel: four warps per
+// number of waves of t(c) each; measured on this pool's B200 per wave: 3.25 ms for 1 per SM (pbs_lat4_kernel: four warps per
 // polynomial), 4.6 ms for 2 (pbs_lat_kernel<2>: two warps per polynomial), 6.35 ms for 3 and 6.75 ms for 4 (pbs_kernel5).
 // A batch is served either by ONE launch with the fewest ciphertexts per CTA that still fits it into the minimum number of
 // waves, or by a launch of full 4-per-SM waves followed by a second launch for the remainder with the kernel that suits the
-// remainder (700 = 592 + 108: 6.75 + 3.7 ms instead of two waves of 3 per SM = 12.7 ms) -- whichever the wave model says is
+// remainder (700 = 592 + 108: 6.75 + 3.25 ms instead of two waves of 3 per SM = 12.7 ms) -- whichever the wave model says is
 // shorter.
-struct PbsWaveModel { double t1 = 3.7, t2 = 4.6, t3 = 6.35, t4 = 6.75, split_penalty = 0.15; };
+struct PbsWaveModel { double t1 = 3.25, t2 = 4.6, t3 = 6.35, t4 = 6.75, split_penalty = 0.15; };
 inline int pbs_per_cta(long long batch, long long sms) {
     const long long waves = (batch + 4 * sms - 1) / (4 * sms);
     return (int)((batch + waves * sms - 1) / (waves * sms));
@@ -275,7 +274,7 @@ void launch_pbs_one(DevCtx &d, const PbsArgs &a, int per_cta) {
         case 1: cudaFuncSetAttribute(pbs_lat_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_lat_smem_bytes<1, true>());
                 pbs_lat_kernel<1, true><<<(unsigned)a.batch, 128, pbs_lat_smem_bytes<1, true>(), d.stream>>>(a); break;
 #else
-        case 1: pbs_lat4t_kernel<<<(unsigned)a.batch, 256, pbs_lat4_smem_bytes(), d.stream>>>(a); break;
+        case 1: pbs_lat4_kernel<<<(unsigned)a.batch, 256, pbs_lat4_smem_bytes(), d.stream>>>(a); break;
 #endif
         case 2: pbs_lat_kernel<2><<<(unsigned)((a.batch + 1) / 2), 256, pbs_lat_smem_bytes<2>(), d.stream>>>(a); break;
         case 3: pbs_kernel5<3><<<(unsigned)((a.batch + 2) / 3), 192, pbs5_smem_bytes<3>(), d.stream>>>(a); break;

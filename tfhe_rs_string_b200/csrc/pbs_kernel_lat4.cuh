@@ -2,21 +2,25 @@
 // polynomial (same contract and reference citations as pbs_kernel5.cuh; used for batches of at most one ciphertext per SM).
 //
 // A CMUX step is a serial dependency chain.  pbs_lat_kernel<1, true> gives a polynomial two warps (16 points per thread) and
-// needs 9.2k cycles per step of which 3k are FP64 issue: the rest is the latency of the chain itself.  Here thread
-// (lane l, quarter r) owns the 8 folded points l + 32 m, m in [8 r, 8 r + 8), so every link of the chain is half as long, and
-// the two warps that share an SM sub-partition (polynomial 0 and 1, same quarter) fill each other's latencies:
-//   forward 32-point pass  = cross-warp radix-4 stage (decimation in frequency)  t_r[mm] = sum_q W4^(q r) x_q[mm],
-//                            times W32^(mm r), then an 8-point transform in registers -> outputs with index 4 kappa + r
-//   inverse 32-point pass  = 8-point transform on the inputs with index 4 kappa + r, times conj(W32^(mm r)), then the
-//                            cross-warp stage  y_q[mm] = sum_r conj(W4^(q r)) u_r[mm]  (decimation in time)
-// The 8 values cross between the four warps through shared memory (two alternating buffers, one 128-thread barrier per
-// pass); the lane <-> register transposition between the passes stays as in fft.cuh.  The frequency layout is unchanged:
-// thread (lane k1, r) holds F[k1 + 32 (4 kappa + r)], so the Fourier BSK of bsk_to_fourier_kernel is used as is.
-// The accumulator (G = -acc, pbs_kernel5.cuh) and the inter-pass twiddles stay in REGISTERS for the whole bootstrap: with 8
-// points per thread there is room, and no tensor-memory round trip is left on the chain.  tools/proto_fft8x4.py is the numpy
-// model of this data flow.
+// needs 9.2k cycles per step of which 3k are FP64 issue: the rest is the latency of the chain itself.  Here a thread owns 8 folded
+// points, so every link of the chain is half as long.  The accumulator (G = -acc, pbs_kernel5.cuh) and the inter-pass twiddles
+// stay in REGISTERS for the whole bootstrap.  A 32-point pass is a cross-warp radix-4 stage, done as two radix-2 levels, plus an
+// 8-point transform in registers; the lane <-> register transposition between the passes stays as in fft.cuh and the frequency
+// layout is unchanged (thread (lane k1, residue r) holds F[k1 + 32 (4 kappa + r)]), so the Fourier BSK of bsk_to_fourier_kernel is
+// used as is.  tools/proto_fft8x4.py is the numpy model of this data flow.
 //
-// Mapping: 8 warps per CTA; warp w: quarter r = w & 3 (= its SM sub-partition), polynomial p = w >> 2.
+// Mapping: warp w = 4 e + 2 p + c holds the input quarter q = c + 2 e (folded points lane + 32 m, m in [8 q, 8 q + 8)) of
+// polynomial p and produces the output residue r = 2 c + e.  The two warps of a tensor-memory quadrant (w and w + 4, which also
+// share an SM sub-partition) hold quarters q and q + 2 of the SAME polynomial, so the level with butterfly distance 16 is a
+// lane-private exchange through 32 TMEM columns and only the level with distance 8 (c <-> 1 - c) goes through shared memory:
+//   forward:  level 1 (TMEM, e = 0 / 1):  a = x_q + x_(q+2)   /   b = (x_q - x_(q+2)) W32^(mm + 8 c)
+//             level 2 (smem, c = 0 / 1):  s0 + s1              /   (s0 - s1) W32^(2 mm);   8-point transform -> outputs 4 kappa + 2 c + e
+//   inverse:  8-point transform on the inputs 4 kappa + 2 c + e;  level 2: c = 1 publishes u conj(W32^(2 mm)), result own +- other;
+//             level 1: e = 1 publishes s conj(W32^(mm + 8 c)), result own +- other  -> index mm + 8 (c + 2 e)
+// (The first version of this kernel did the radix-4 stage in one go through shared memory, every thread reading the three foreign
+// quarters: 832 shared-memory wavefronts per warp and step, 74 % of the SM's shared-memory pipe, 3.68 ms per bootstrap level.  With
+// one level in tensor memory it is 576 wavefronts and 3.43 ms; refilling the BSK slice by one thread right after the CTA barrier
+// that already follows the last read of the slice -- instead of a consumer counter whose atomic returns after ~250 cycles -- 3.24.)
 #pragma once
 #include "pbs_kernel5.cuh"
 
@@ -47,331 +51,10 @@ __host__ __device__ constexpr size_t pbs_lat4_smem_bytes() {
 __device__ __forceinline__ void poly_barrier(const int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void cta_barrier256(const int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 
-// acc += s * v with s a power of W4 = -i (forward) : kS = 0: +v, 1: -i v, 2: -v, 3: +i v
-template <int kS>
-__device__ __forceinline__ void acc_w4(double &tr, double &ti, const double vr, const double vi) {
-    if (kS == 0) { tr += vr; ti += vi; }
-    else if (kS == 1) { tr += vi; ti -= vr; }
-    else if (kS == 2) { tr -= vr; ti -= vi; }
-    else { tr -= vi; ti += vr; }
-}
-// y = x * W32^kE (kConj: times the conjugate), kE in [0, 32)
-template <int kE, bool kConj>
-__device__ __forceinline__ void mul_w32(double &xr, double &xi) {
-    constexpr int e = kE & 31;
-    if (e == 0) return;
-    if (e == 16) { xr = -xr; xi = -xi; return; }
-    if (e == 8 || e == 24) {   // W32^8 = -i, W32^24 = +i
-        const bool plus_i = (e == 24) != kConj;
-        const double r = xr, i2 = xi;
-        xr = plus_i ? -i2 : i2; xi = plus_i ? r : -r;
-        return;
-    }
-    constexpr int t = e & 15;
-    const double sg = e >= 16 ? -1.0 : 1.0;
-    const double wr = sg * w32_re(t), wi = (kConj ? -sg : sg) * w32_im(t);
-    const double nr = fma(-xi, wi, xr * wr);
-    xi = fma(xi, wr, xr * wi);
-    xr = nr;
-}
-
-// forward cross-warp stage of warp kR: own values x (quarter kR), the three others from the exchange buffer `ex`
-// ([quarter][mm][lane], already offset by the lane); result in bit-reversed register order for fft8_dit
-template <int kR>
-__device__ __forceinline__ void lat4_fwd_combine(const double (&xr)[8], const double (&xi)[8], const double2 *ex, double (&yr)[8], double (&yi)[8]) {
-#pragma unroll
-    for (int mm = 0; mm < 8; mm++) {
-        double2 v[3][8];
-#pragma unroll
-        for (int d = 0; d < 3; d++) v[d][mm] = ex[(((kR + 1 + d) & 3) * 8 + mm) * 32];
-        double tr = xr[mm], ti = xi[mm];
-        if (kR & 1) {   // own term W4^(kR * kR): 1 for even kR, W4^1 = -i for kR = 1, W4^9 = -i for kR = 3
-            tr = xi[mm]; ti = -xr[mm];
-        }
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const int q = (kR + 1 + d) & 3;
-            switch ((q * kR) & 3) {
-                case 0: acc_w4<0>(tr, ti, v[d][mm].x, v[d][mm].y); break;
-                case 1: acc_w4<1>(tr, ti, v[d][mm].x, v[d][mm].y); break;
-                case 2: acc_w4<2>(tr, ti, v[d][mm].x, v[d][mm].y); break;
-                default: acc_w4<3>(tr, ti, v[d][mm].x, v[d][mm].y); break;
-            }
-        }
-        switch (mm) {   // times W32^(mm kR)
-            case 1: mul_w32<1 * kR, false>(tr, ti); break;
-            case 2: mul_w32<2 * kR, false>(tr, ti); break;
-            case 3: mul_w32<3 * kR, false>(tr, ti); break;
-            case 4: mul_w32<4 * kR, false>(tr, ti); break;
-            case 5: mul_w32<5 * kR, false>(tr, ti); break;
-            case 6: mul_w32<6 * kR, false>(tr, ti); break;
-            case 7: mul_w32<7 * kR, false>(tr, ti); break;
-            default: break;
-        }
-        yr[brev3(mm)] = tr; yi[brev3(mm)] = ti;
-    }
-}
-// inverse: u = conj(W32^(mm kR)) * x (what warp kR publishes)
-template <int kR>
-__device__ __forceinline__ void lat4_inv_twiddle(double (&xr)[8], double (&xi)[8]) {
-    mul_w32<1 * kR, true>(xr[1], xi[1]); mul_w32<2 * kR, true>(xr[2], xi[2]); mul_w32<3 * kR, true>(xr[3], xi[3]);
-    mul_w32<4 * kR, true>(xr[4], xi[4]); mul_w32<5 * kR, true>(xr[5], xi[5]); mul_w32<6 * kR, true>(xr[6], xi[6]);
-    mul_w32<7 * kR, true>(xr[7], xi[7]);
-}
-// inverse cross-warp stage of warp kQ: y[mm] = sum_r conj(W4^(kQ r)) u_r[mm]  (own u in registers)
-template <int kQ>
-__device__ __forceinline__ void lat4_inv_combine(const double (&ur)[8], const double (&ui)[8], const double2 *ex, double (&yr)[8], double (&yi)[8]) {
-#pragma unroll
-    for (int mm = 0; mm < 8; mm++) {
-        double2 v[3][8];
-#pragma unroll
-        for (int d = 0; d < 3; d++) v[d][mm] = ex[(((kQ + 1 + d) & 3) * 8 + mm) * 32];
-        double tr = ur[mm], ti = ui[mm];
-        if (kQ & 1) {   // own term conj(W4^(kQ kQ)) = +i for odd kQ
-            tr = -ui[mm]; ti = ur[mm];
-        }
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const int r = (kQ + 1 + d) & 3;
-            switch ((4 - ((kQ * r) & 3)) & 3) {   // conj(W4^s) = W4^(4 - s)
-                case 0: acc_w4<0>(tr, ti, v[d][mm].x, v[d][mm].y); break;
-                case 1: acc_w4<1>(tr, ti, v[d][mm].x, v[d][mm].y); break;
-                case 2: acc_w4<2>(tr, ti, v[d][mm].x, v[d][mm].y); break;
-                default: acc_w4<3>(tr, ti, v[d][mm].x, v[d][mm].y); break;
-            }
-        }
-        yr[mm] = tr; yi[mm] = ti;
-    }
-}
-
-// forward pass of warp r (warp-uniform dispatch on the quarter): publish x, barrier, combine + twiddle, 8-point transform
-__device__ __forceinline__ void lat4_fwd_pass(const double (&xr)[8], const double (&xi)[8], double (&yr)[8], double (&yi)[8], const int r,
-                                              double2 *ex, const int bar) {
-#pragma unroll
-    for (int mm = 0; mm < 8; mm++) ex[(r * 8 + mm) * 32] = make_double2(xr[mm], xi[mm]);
-    poly_barrier(bar);
-    switch (r) {
-        case 0: lat4_fwd_combine<0>(xr, xi, ex, yr, yi); break;
-        case 1: lat4_fwd_combine<1>(xr, xi, ex, yr, yi); break;
-        case 2: lat4_fwd_combine<2>(xr, xi, ex, yr, yi); break;
-        default: lat4_fwd_combine<3>(xr, xi, ex, yr, yi); break;
-    }
-    fft8_dit<false>(yr, yi);
-}
-// inverse pass: x[brev3(kappa)] = inputs 4 kappa + r -> y[mm] = result for index mm + 8 r
-__device__ __forceinline__ void lat4_inv_pass(double (&xr)[8], double (&xi)[8], double (&yr)[8], double (&yi)[8], const int r,
-                                              double2 *ex, const int bar) {
-    fft8_dit<true>(xr, xi);
-    switch (r) {
-        case 0: break;
-        case 1: lat4_inv_twiddle<1>(xr, xi); break;
-        case 2: lat4_inv_twiddle<2>(xr, xi); break;
-        default: lat4_inv_twiddle<3>(xr, xi); break;
-    }
-#pragma unroll
-    for (int mm = 0; mm < 8; mm++) ex[(r * 8 + mm) * 32] = make_double2(xr[mm], xi[mm]);
-    poly_barrier(bar);
-    switch (r) {
-        case 0: lat4_inv_combine<0>(xr, xi, ex, yr, yi); break;
-        case 1: lat4_inv_combine<1>(xr, xi, ex, yr, yi); break;
-        case 2: lat4_inv_combine<2>(xr, xi, ex, yr, yi); break;
-        default: lat4_inv_combine<3>(xr, xi, ex, yr, yi); break;
-    }
-}
-
-__global__ void __launch_bounds__(256, 1) pbs_lat4_kernel(const PbsArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = warp & 3, p = warp >> 2;
-    const int ct = blockIdx.x;
-    if (ct >= a.batch) return;   // (CTA-uniform)
-
-    uint64_t *bsk_bar = reinterpret_cast<uint64_t *>(smem + 8);
-    unsigned int *consumed = reinterpret_cast<unsigned int *>(smem + 16);
-    double2 *bsk_s = reinterpret_cast<double2 *>(smem + kPbsHeaderBytes);
-    unsigned char *pbase = smem + kPbsHeaderBytes + kBskSliceBytes + (size_t)p * kLat4PolyBytes;
-    unsigned char *obase = smem + kPbsHeaderBytes + kBskSliceBytes + (size_t)(1 - p) * kLat4PolyBytes;
-    double2 *tb_own = reinterpret_cast<double2 *>(pbase);                      // shared by the four warps of the polynomial
-    const double2 *tb_oth = reinterpret_cast<const double2 *>(obase);
-    double2 *ex0 = reinterpret_cast<double2 *>(pbase + kBuf5Bytes) + lane, *ex1 = ex0 + kLat4ExBytes / (int)sizeof(double2);
-    uint16_t *ahat = reinterpret_cast<uint16_t *>(smem + kPbsHeaderBytes + kBskSliceBytes + (size_t)2 * kLat4PolyBytes);
-    uint64_t *rot = reinterpret_cast<uint64_t *>(tb_own);   // rotation copy (G = -acc, + overflow zone, pbs_kernel5.cuh) aliases the transposition buffer
-    const int bar_poly = 1 + p, bar_ct = 3;
-
-    if (threadIdx.x == 0) {
-        mbar_init(bsk_bar, 1);
-        *consumed = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) issue_bsk_slice(bsk_s, a.bsk, 0, bsk_bar);
-
-    // this thread's inter-pass twiddles T'[4 kappa + r][lane]
-    double twr[8], twi[8];
-#pragma unroll
-    for (int kap = 0; kap < 8; kap++) {
-        const double2 t = __ldg(a.twid + (4 * kap + r) * 32 + lane);
-        twr[kap] = t.x; twi[kap] = t.y;
-    }
-
-    // ---------------------------------------------------------------- prologue
-    const uint64_t *lwe = a.lwe_small + (size_t)ct * (a.n + 1);
-    for (int i = threadIdx.x; i < a.n; i += 256) ahat[i] = (uint16_t)modswitch2048(lwe[i]);
-    const uint32_t bhat = modswitch2048(lwe[a.n]);
-    const uint64_t *lut = a.luts + ((size_t)pbs_lut_id(a, ct) * 2 + p) * kN;
-    // acc = LUT * X^-b~ (polynomial_algorithms.rs:315-354); the registers and the rotation copy hold G = -acc
-    uint64_t g0[8], g1[8];
-#pragma unroll
-    for (int mm = 0; mm < 8; mm++) {
-        const int j = lane + 32 * (8 * r + mm);
-        const uint32_t i0 = (uint32_t)(j + bhat) & 4095u, i1 = (i0 + 1024u) & 4095u;
-        uint64_t v0 = lut[i0 & 2047u], v1 = lut[i1 & 2047u];
-        if (i0 & 2048u) v0 = 0 - v0;
-        if (i1 & 2048u) v1 = 0 - v1;
-        g0[mm] = 0 - v0; g1[mm] = 0 - v1;
-        rot[j] = g0[mm]; rot[j + kHalf] = g1[mm];
-        if (j < kZone5) rot[kN + j] = v0;
-    }
-    cta_barrier256(bar_ct);   // a~ table and both rotation copies complete
-
-    // ---------------------------------------------------------------- CMUX loop
-    for (int i = 0; i < a.n; i++) {
-        PBS3_TS(0);
-        double xr[8], xi[8], yr[8], yi[8];
-        // phase A: ct1 = acc * X^a~ - acc, round + digit, exact int -> double, twist by C_m (group-uniform gather of
-        // pbs_kernel5.cuh: this thread's slots 8 r .. 8 r + 7 are group r of the first half and group 4 + r of the second)
-        {
-            const uint32_t q0 = (4096u - (uint32_t)ahat[i]) & 4095u;
-            const uint32_t qa = (q0 + 256u * (uint32_t)r) & 4095u, qb = (qa + 1024u) & 4095u;
-            const uint64_t *pa = rot + lane + (qa & 2047u), *pb = rot + lane + (qb & 2047u);
-            const uint32_t ta = (qa >> 11) - 1u, tb = (qb >> 11) - 1u;
-            const uint64_t ma = pack64(ta, ta), mb = pack64(tb, tb), ca = pack64(ta & 1u, 0x7FFFFF00u), cb = pack64(tb & 1u, 0x7FFFFF00u);
-#pragma unroll
-            for (int mm = 0; mm < 8; mm++) {
-                const uint64_t e0 = g0[mm] + (pa[32 * mm] ^ ma) + ca;
-                const uint64_t e1 = g1[mm] + (pb[32 * mm] ^ mb) + cb;
-                const double fr = dbl((uint32_t)(e0 >> 41), 0x43300000u) - 4503599631564799.0;
-                const double fi = dbl((uint32_t)(e1 >> 41), 0x43300000u) - 4503599631564799.0;
-                const double2 cm = c_twm[8 * r + mm];
-                xr[mm] = fma(-fi, cm.y, fr * cm.x);
-                xi[mm] = fma(fi, cm.x, fr * cm.y);
-            }
-        }
-        PBS3_TS(1);
-        // ---- forward transform (the barrier inside the first pass also orders all rotation reads before the buffer is reused)
-        lat4_fwd_pass(xr, xi, yr, yi, r, ex0, bar_poly);
-#pragma unroll
-        for (int kap = 0; kap < 8; kap++) {
-            const double nr = fma(-yi[kap], twi[kap], yr[kap] * twr[kap]);
-            const double ni = fma(yi[kap], twr[kap], yr[kap] * twi[kap]);
-            tb_own[lane * kTStride + 4 * kap + r] = make_double2(nr, ni);
-        }
-        PBS3_TS(2);
-        poly_barrier(bar_poly);
-#pragma unroll
-        for (int ll = 0; ll < 8; ll++) {
-            const double2 v = tb_own[(ll + 8 * r) * kTStride + lane];
-            xr[ll] = v.x; xi[ll] = v.y;
-        }
-        lat4_fwd_pass(xr, xi, yr, yi, r, ex1, bar_poly);   // its barrier also orders the transposition reads before the writes below
-        PBS3_TS(3);
-
-        // ---- exchange the transforms between the two polynomials, Out_p = B[p][p] F_p + B[1-p][p] F_{1-p}
-#pragma unroll
-        for (int kap = 0; kap < 8; kap++) tb_own[(4 * kap + r) * 32 + lane] = make_double2(yr[kap], yi[kap]);
-        mbar_wait(bsk_bar, (uint32_t)(i & 1));
-        double zr[8], zi[8];
-        {
-            const double2 *b_own = bsk_s + (size_t)(p * 2 + p) * kHalf + lane;
-#pragma unroll
-            for (int kap = 0; kap < 8; kap++) {
-                const double2 bo = b_own[(4 * kap + r) * 32];
-                zr[brev3(kap)] = fma(-bo.y, yi[kap], bo.x * yr[kap]);
-                zi[brev3(kap)] = fma(bo.y, yr[kap], bo.x * yi[kap]);
-            }
-        }
-        PBS3_TS(4);
-        cta_barrier256(bar_ct);
-        PBS3_TS(5);
-        {
-            const double2 *b_oth = bsk_s + (size_t)((1 - p) * 2 + p) * kHalf + lane;
-#pragma unroll
-            for (int kap = 0; kap < 8; kap++) {
-                const int q = 4 * kap + r;
-                const double2 bx = b_oth[q * 32], g = tb_oth[q * 32 + lane];
-                const double o_r = fma(bx.x, g.x, zr[brev3(kap)]), o_i = fma(bx.x, g.y, zi[brev3(kap)]);
-                zr[brev3(kap)] = fma(-bx.y, g.y, o_r); zi[brev3(kap)] = fma(bx.y, g.x, o_i);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {   // this warp is done with the slice; the last of the CTA's warps refills the buffer
-            const unsigned int old = atomicAdd(consumed, 1u);
-            if (old == (unsigned int)(i + 1) * 8u - 1u && i + 1 < a.n)
-                issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
-        }
-        PBS3_TS(6);
-        cta_barrier256(bar_ct);   // the sibling polynomial has read this one's transform before the buffer is reused
-        PBS3_TS(7);
-
-        // ---- inverse transform
-        lat4_inv_pass(zr, zi, yr, yi, r, ex0, bar_poly);   // y[ll]: index l = ll + 8 r of lane k1
-#pragma unroll
-        for (int ll = 0; ll < 8; ll++) tb_own[lane * kTStride + ll + 8 * r] = make_double2(yr[ll], yi[ll]);
-        poly_barrier(bar_poly);
-#pragma unroll
-        for (int kap = 0; kap < 8; kap++) {
-            const double2 v = tb_own[(4 * kap + r) * kTStride + lane];
-            zr[brev3(kap)] = fma(v.y, twi[kap], v.x * twr[kap]);          // times conj(T')
-            zi[brev3(kap)] = fma(v.y, twr[kap], -(v.x * twi[kap]));
-        }
-        lat4_inv_pass(zr, zi, yr, yi, r, ex1, bar_poly);   // its barrier orders the transposition reads before the rotation copy below
-        PBS3_TS(8);
-
-        // ---- phase D: untwist, from_torus, G -= delta (registers), refresh the rotation copy
-#pragma unroll
-        for (int mm = 0; mm < 8; mm++) {
-            const int j = lane + 32 * (mm + 8 * r);
-            const double2 cm = c_twm[8 * r + mm];
-            const double ur = fma(yi[mm], cm.y, yr[mm] * cm.x);
-            const double ui = fma(yi[mm], cm.x, -(yr[mm] * cm.y));
-            g0[mm] = g0[mm] + kFtBias - from_torus_fp(ur);   // acc += delta <=> G -= delta (from_torus on the FP64 pipe, pbs_common.cuh)
-            g1[mm] = g1[mm] + kFtBias - from_torus_fp(ui);
-            rot[j] = g0[mm]; rot[j + kHalf] = g1[mm];
-            if (j < kZone5) rot[kN + j] = 0 - g0[mm];        // (warp-uniform: r == 0)
-        }
-        PBS3_TS(9);
-        poly_barrier(bar_poly);   // rotation copy complete (all four quarters) before the next step's gather
-        PBS3_TS(10);
-    }
-
-    // ---------------------------------------------------------------- sample extraction (acc = -G)
-    uint64_t *o = a.out + (size_t)ct * (kN + 1);
-    if (p == 0) {
-#pragma unroll
-        for (int mm = 0; mm < 8; mm++) {
-            const int j = lane + 32 * (8 * r + mm);
-            if (j == 0) o[0] = 0 - g0[mm]; else o[kN - j] = g0[mm];
-            o[kHalf - j] = g1[mm];   // coefficient j + 1024 -> index N - (j + 1024), negated
-        }
-    } else if (r == 0 && lane == 0) {
-        o[kN] = 0 - g0[0];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------------
-// pbs_lat4t_kernel: the same four-warps-per-polynomial decomposition with the cross-warp radix-4 stage split into two radix-2
-// levels, ONE OF THEM THROUGH TENSOR MEMORY.  pbs_lat4_kernel is bound by the SM's shared-memory pipe (every thread reads three
-// foreign quarters per pass: 832 wavefronts per warp and step).  Here warp w = 4 e + 2 p + c holds the input quarter q = c + 2 e of
-// polynomial p: the two warps of a tensor-memory quadrant (w and w + 4) hold quarters q and q + 2 of the SAME polynomial, so the
-// level with butterfly distance 16 is a lane-private exchange through 32 TMEM columns (no shared-memory traffic), and only the
-// level with distance 8 (c <-> 1 - c) goes through shared memory: one foreign quarter per pass, 576 wavefronts per warp and step.
-//   forward:  level 1 (TMEM, e = 0 / 1):  a = x_q + x_(q+2)   /   b = (x_q - x_(q+2)) W32^(mm + 8 c)
-//             level 2 (smem, c = 0 / 1):  s0 + s1              /   (s0 - s1) W32^(2 mm);   8-point transform -> outputs 4 kappa + 2 c + e
-//   inverse:  8-point transform on the inputs 4 kappa + 2 c + e;  level 2: c = 1 publishes u conj(W32^(2 mm)), result own +- other;
-//             level 1: e = 1 publishes s conj(W32^(mm + 8 c)), result own +- other  -> index mm + 8 (c + 2 e)
 __device__ __forceinline__ void pair_barrier64(const int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // swap 8 complex values with the warp that shares this warp's tensor-memory quadrant (lane-private)
-__device__ __forceinline__ void lat4t_tmem_swap(const double (&vr)[8], const double (&vi)[8], double (&rr)[8], double (&ri)[8],
+__device__ __forceinline__ void lat4_tmem_swap(const double (&vr)[8], const double (&vi)[8], double (&rr)[8], double (&ri)[8],
                                                 const uint32_t xout, const uint32_t xin, const int bar) {
 #pragma unroll
     for (int k = 0; k < 2; k++) {
@@ -400,11 +83,11 @@ __device__ __forceinline__ void lat4t_tmem_swap(const double (&vr)[8], const dou
 }
 
 // forward pass: x = own quarter (natural mm) -> y[kappa] = output 4 kappa + 2 c + e
-__device__ __forceinline__ void lat4t_fwd_pass(const double (&xr)[8], const double (&xi)[8], double (&yr)[8], double (&yi)[8],
+__device__ __forceinline__ void lat4_fwd_pass(const double (&xr)[8], const double (&xi)[8], double (&yr)[8], double (&yi)[8],
                                                const int c, const int e, const uint32_t xout, const uint32_t xin, const int bar_pair,
                                                double2 *ex_own, const double2 *ex_oth, const int bar_poly) {
     double rr[8], ri[8], sr[8], si[8];
-    lat4t_tmem_swap(xr, xi, rr, ri, xout, xin, bar_pair);
+    lat4_tmem_swap(xr, xi, rr, ri, xout, xin, bar_pair);
     const double sg1 = e ? -1.0 : 1.0;   // e = 0: own + other;  e = 1: other - own = x_q - x_(q+2) (own is quarter q + 2)
 #pragma unroll
     for (int mm = 0; mm < 8; mm++) {
@@ -438,7 +121,7 @@ __device__ __forceinline__ void lat4t_fwd_pass(const double (&xr)[8], const doub
     fft8_dit<false>(yr, yi);
 }
 // inverse pass: x[brev3(kappa)] = inputs 4 kappa + 2 c + e -> y[mm] = result for index mm + 8 (c + 2 e)
-__device__ __forceinline__ void lat4t_inv_pass(double (&xr)[8], double (&xi)[8], double (&yr)[8], double (&yi)[8],
+__device__ __forceinline__ void lat4_inv_pass(double (&xr)[8], double (&xi)[8], double (&yr)[8], double (&yi)[8],
                                                const int c, const int e, const uint32_t xout, const uint32_t xin, const int bar_pair,
                                                double2 *ex_own, const double2 *ex_oth, const int bar_poly) {
     fft8_dit<true>(xr, xi);
@@ -471,7 +154,7 @@ __device__ __forceinline__ void lat4t_inv_pass(double (&xr)[8], double (&xi)[8],
         sr[mm] = tr; si[mm] = ti;
     }
     double rr[8], ri[8];
-    lat4t_tmem_swap(sr, si, rr, ri, xout, xin, bar_pair);
+    lat4_tmem_swap(sr, si, rr, ri, xout, xin, bar_pair);
     const double sg1 = e ? -1.0 : 1.0;   // e = 0: own + other';  e = 1: other - own'
 #pragma unroll
     for (int mm = 0; mm < 8; mm++) {
@@ -480,7 +163,7 @@ __device__ __forceinline__ void lat4t_inv_pass(double (&xr)[8], double (&xi)[8],
     }
 }
 
-__global__ void __launch_bounds__(256, 1) pbs_lat4t_kernel(const PbsArgs a) {
+__global__ void __launch_bounds__(256, 1) pbs_lat4_kernel(const PbsArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = warp & 1, p = (warp >> 1) & 1, e = warp >> 2;
@@ -567,7 +250,7 @@ __global__ void __launch_bounds__(256, 1) pbs_lat4t_kernel(const PbsArgs a) {
         }
         PBS3_TS(1);
         // ---- forward transform (the barriers inside the first pass also order all rotation reads before the buffer is reused)
-        lat4t_fwd_pass(xr, xi, yr, yi, c, e, tx0_out, tx0_in, bar_pair, ex0_own, ex0_oth, bar_poly);
+        lat4_fwd_pass(xr, xi, yr, yi, c, e, tx0_out, tx0_in, bar_pair, ex0_own, ex0_oth, bar_poly);
 #pragma unroll
         for (int kap = 0; kap < 8; kap++) {
             const double nr = fma(-yi[kap], twi[kap], yr[kap] * twr[kap]);
@@ -581,7 +264,7 @@ __global__ void __launch_bounds__(256, 1) pbs_lat4t_kernel(const PbsArgs a) {
             const double2 v = tb_own[(ll + 8 * q) * kTStride + lane];
             xr[ll] = v.x; xi[ll] = v.y;
         }
-        lat4t_fwd_pass(xr, xi, yr, yi, c, e, tx1_out, tx1_in, bar_pair, ex1_own, ex1_oth, bar_poly);   // its poly barrier orders the transposition reads before the writes below
+        lat4_fwd_pass(xr, xi, yr, yi, c, e, tx1_out, tx1_in, bar_pair, ex1_own, ex1_oth, bar_poly);   // its poly barrier orders the transposition reads before the writes below
         PBS3_TS(3);
 
         // ---- exchange the transforms between the two polynomials, Out_p = B[p][p] F_p + B[1-p][p] F_{1-p}
@@ -618,7 +301,7 @@ __global__ void __launch_bounds__(256, 1) pbs_lat4t_kernel(const PbsArgs a) {
         PBS3_TS(7);
 
         // ---- inverse transform
-        lat4t_inv_pass(zr, zi, yr, yi, c, e, tx0_out, tx0_in, bar_pair, ex0_own, ex0_oth, bar_poly);   // y[ll]: index l = ll + 8 q of lane k1
+        lat4_inv_pass(zr, zi, yr, yi, c, e, tx0_out, tx0_in, bar_pair, ex0_own, ex0_oth, bar_poly);   // y[ll]: index l = ll + 8 q of lane k1
 #pragma unroll
         for (int ll = 0; ll < 8; ll++) tb_own[lane * kTStride + ll + 8 * q] = make_double2(yr[ll], yi[ll]);
         poly_barrier(bar_poly);
@@ -628,7 +311,7 @@ __global__ void __launch_bounds__(256, 1) pbs_lat4t_kernel(const PbsArgs a) {
             zr[brev3(kap)] = fma(v.y, twi[kap], v.x * twr[kap]);          // times conj(T')
             zi[brev3(kap)] = fma(v.y, twr[kap], -(v.x * twi[kap]));
         }
-        lat4t_inv_pass(zr, zi, yr, yi, c, e, tx1_out, tx1_in, bar_pair, ex1_own, ex1_oth, bar_poly);   // its poly barrier orders the transposition reads before the rotation copy below
+        lat4_inv_pass(zr, zi, yr, yi, c, e, tx1_out, tx1_in, bar_pair, ex1_own, ex1_oth, bar_poly);   // its poly barrier orders the transposition reads before the rotation copy below
         PBS3_TS(8);
 
         // ---- phase D: untwist, from_torus, G -= delta (registers), refresh the rotation copy

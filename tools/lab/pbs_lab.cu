@@ -87,10 +87,6 @@ int main(int argc, char **argv) {
             CK(cudaFuncSetAttribute(pbs_lat4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_lat4_smem_bytes()));
             pbs_lat4_kernel<<<x.batch, 256, pbs_lat4_smem_bytes(), 0>>>(x);
         }
-        else if (kernel == 75) {   // the same with one radix-2 level of the cross-warp stage through tensor memory
-            CK(cudaFuncSetAttribute(pbs_lat4t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_lat4_smem_bytes()));
-            pbs_lat4t_kernel<<<x.batch, 256, pbs_lat4_smem_bytes(), 0>>>(x);
-        }
         else if (kernel == 72) launch_lat<1, true>(x, 0);   // one ciphertext per SM, the halves of a polynomial on different sub-partitions
         else if (kernel == 5) {
             switch (cts) { case 1: launch5<1>(x, 0); break; case 2: launch5<2>(x, 0); break; case 3: launch5<3>(x, 0); break; default: launch5<4>(x, 0); }
