@@ -90,9 +90,9 @@ def test_from_torus_fp_pipe_is_exact(engine):
     assert np.all(want[diff] == U64(1 << 63)) and np.all(cvt[diff] == U64((1 << 63) - 1))
 
 
-# 200 -> pbs_lat_kernel<2>, 400 -> pbs_kernel5<3>, 500 -> pbs_kernel5<4> (one wave), 1024 -> pbs_kernel5<4> (two waves,
+# 3 and 148 -> pbs_lat4_kernel too (a tail of three CTAs; every SM busy), 200 -> pbs_lat_kernel<2>, 400 -> pbs_kernel5<3>, 500 -> pbs_kernel5<4> (one wave), 1024 -> pbs_kernel5<4> (two waves,
 # BASELINE configs[0]): the throughput kernel that the benchmark times is compared with the oracle like the others.
-@pytest.mark.parametrize("batch", [40, 200, 400, 500, 1024])
+@pytest.mark.parametrize("batch", [3, 40, 148, 200, 400, 500, 1024])
 def test_pbs_parity(engine, real_keys, batch):
     msgs = np.arange(batch) % 32          # includes padding-bit-set inputs (negacyclic branch)
     cts = real_keys.encrypt_batch(msgs, seed=300 + batch)
@@ -113,7 +113,8 @@ def test_pbs_parity(engine, real_keys, batch):
     ideal = np.array(exp, dtype=U64) * U64(real_keys.params.delta)
     e_gpu = (real_keys.phase_batch(got) - ideal).astype(np.int64).astype(np.float64)
     e_ref = (real_keys.phase_batch(ref) - ideal).astype(np.int64).astype(np.float64)
-    assert 0.6 < e_gpu.std() / e_ref.std() < 1.6, (e_gpu.std(), e_ref.std())
+    if batch >= 40:   # (a spread over three samples says nothing)
+        assert 0.6 < e_gpu.std() / e_ref.std() < 1.6, (e_gpu.std(), e_ref.std())
     assert np.abs(e_gpu).max() < (1 << 54)
     # the separate entry points give the same bits as the fused call (same kernels, same order)
     if batch <= 200:
