@@ -41,7 +41,7 @@ typedef struct b200tfhe_ctx b200tfhe_ctx;
  * Every classic parameter set of the reference is accepted: glwe_dimension 1..8, polynomial_size 256..32768,
  * any PBS / KS decomposition with base_log*level < 64, lwe_dimension <= 4096.  Sets with glwe_dimension = 1,
  * polynomial_size = 2048, pbs_level = 1, pbs_base_log = 23 (PARAM_MESSAGE_1_CARRY_3, 2_2, 3_1, 4_0 _KS_PBS and
- * 2_2 _PBS_KS, shortint/parameters/mod.rs:688-747,1155-1169) run on the specialised kernels (pbs_kernel3 /
+ * 2_2 _PBS_KS, shortint/parameters/mod.rs:688-747,1155-1169) run on the specialised kernels (pbs_kernel5 / pbs_lat4_kernel /
  * pbs_lat_kernel); all others (1_1 k=3 N=512 :613-627, 3_3 N=8192 l=2 :853-867, 4_4 N=32768 :1063-1077, ...) on the
  * generic one-CTA-per-ciphertext kernel (csrc/pbs_generic.cuh). */
 typedef struct {
