@@ -49,6 +49,25 @@ __host__ __device__ constexpr size_t pbs5_smem_bytes() {
 #define PBS5_TWFOLD 0
 #endif
 
+// The BSK slice is refilled in two halves, each with its own mbarrier and consumer counter: the diagonal polynomials B[p][p] as
+// soon as every warp of the CTA has done its own product, the off-diagonal ones after the sibling products (kSplit = 1) or
+// already before the inverse first pass (kSplit = 2).  The four ciphertexts of a CTA drift up to 0.7 of a step apart and are
+// coupled only through this buffer: a refill that waits for the slowest warp's LAST use of the whole slice lands late for the
+// fastest one.  Measured per 4096 bootstraps: one refill 46.4 ms, two halves 44.7 ms (4 per SM); 3 per SM: 6.34 / 6.25 / 6.09 ms
+// per 444 for kSplit = 0 / 1 / 2.  -1 = that choice per kCts; 0, 1, 2 force one (tools/lab).
+#ifndef PBS5_SPLIT_BSK
+#define PBS5_SPLIT_BSK -1
+#endif
+template <int kCts> __host__ __device__ constexpr int pbs5_split() { return PBS5_SPLIT_BSK >= 0 ? PBS5_SPLIT_BSK : (kCts == 3 ? 2 : 1); }
+// one thread: fetch half `which` (0: polynomials (0,0) and (1,1), 1: (0,1) and (1,0)) of the Fourier BSK slice of CMUX step i
+__device__ __forceinline__ void issue_bsk_half(double2 *bsk_s, const double2 *bsk_g, const int i, const int which, uint64_t *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive_expect_tx(bar, (uint32_t)kBskSliceBytes / 2);
+    const double2 *src = bsk_g + (size_t)i * 4 * kHalf;
+    const int p0 = which ? 1 : 0, p1 = which ? 2 : 3;
+    bulk_g2s(bsk_s + p0 * kHalf, src + p0 * kHalf, kBskSliceBytes / 4, bar);   // (two copies of 8 KB per polynomial: -0.6 %, four: +1.2 %)
+    bulk_g2s(bsk_s + p1 * kHalf, src + p1 * kHalf, kBskSliceBytes / 4, bar);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
@@ -211,6 +230,8 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
     uint32_t *slot = reinterpret_cast<uint32_t *>(smem);
     uint64_t *bsk_bar = reinterpret_cast<uint64_t *>(smem + 8);
     unsigned int *consumed = reinterpret_cast<unsigned int *>(smem + 16);
+    uint64_t *bsk_bar_o = reinterpret_cast<uint64_t *>(smem + 96);            // PBS5_SPLIT_BSK: off-diagonal half
+    unsigned int *consumed_o = reinterpret_cast<unsigned int *>(smem + 104);
     uint64_t *bar_free = reinterpret_cast<uint64_t *>(smem + 32) + 2 * ctl;   // both warps are done reading their own buffer
     uint64_t *bar_full = bar_free + 1;                                        // both warps have written their transform
     double2 *bsk_s = reinterpret_cast<double2 *>(smem + kHdr5Bytes);
@@ -223,9 +244,14 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
     // ---------------------------------------------------------------- CTA setup
     constexpr uint32_t kTmemCols = kCts <= 2 ? 256u : 512u;   // twiddles + 128 accumulator columns per warp of a quadrant
     if (warp == 0) tmem_alloc(slot, kTmemCols);
+    constexpr int kSplit = pbs5_split<kCts>();
     if (threadIdx.x == 0) {
         mbar_init(bsk_bar, 1);
         *consumed = 0;
+        if (kSplit) {
+            mbar_init(bsk_bar_o, 1);
+            *consumed_o = 0;
+        }
     }
     if (lane == 0 && p == 0) {
         mbar_init(bar_free, 2);
@@ -252,7 +278,10 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
     const unsigned int n_act_warps = 2u * (unsigned int)n_act_cts;
     const bool dephase = kPhase > 0 && kCts == 4 && n_act_cts == 4;   // CTA-uniform
     const bool late = warp >= 4;
-    if (threadIdx.x == 0) issue_bsk_slice(bsk_s, a.bsk, 0, bsk_bar);
+    if (threadIdx.x == 0) {
+        if (kSplit) { issue_bsk_half(bsk_s, a.bsk, 0, 0, bsk_bar); issue_bsk_half(bsk_s, a.bsk, 0, 1, bsk_bar_o); }
+        else issue_bsk_slice(bsk_s, a.bsk, 0, bsk_bar);
+    }
     tmem_fence_before();
     __syncthreads();
     tmem_fence_after();
@@ -421,12 +450,18 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full);
+            if (kSplit && lane == 0) {   // this warp is done with the diagonal half; the last of the CTA's warps refills it
+                const unsigned int old = atomicAdd(consumed, 1u);
+                if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
+                    issue_bsk_half(bsk_s, a.bsk, i + 1, 0, bsk_bar);
+            }
             if (dephase) {
                 if (!late) bar_arrive(5, 256);
                 else if (i + 1 < a.n) bar_arrive(6, 256);
             }
             PBS5_TS(5);
             mbar_wait(bar_full, par);
+            if (kSplit) mbar_wait(bsk_bar_o, par);
             PBS5_TS(6);
             {
                 const double2 *b_oth = bsk_s + (size_t)((1 - p) * 2 + p) * kHalf + lane;   // row 1-p, column p
@@ -443,16 +478,30 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
                     fft32_dit_df<true, 0, 32>(zr, zi, oth);   // inverse first pass (registers only), products at the leaves
                 } else {
                     sibling_products<0, kXT>(zr, zi, oth);
+                    if (kSplit == 2) {   // off-diagonal half released BEFORE the inverse first pass
+                        __syncwarp();
+                        if (lane == 0) {
+                            const unsigned int old = atomicAdd(consumed_o, 1u);
+                            if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
+                                issue_bsk_half(bsk_s, a.bsk, i + 1, 1, bsk_bar_o);
+                        }
+                    }
                     inv1024_pass1(zr, zi);
                 }
             }
             PBS5_TS(7);
             // this warp is done with the slice (and with the sibling's transform); the last of the CTA's warps refills the slice buffer
             __syncwarp();
-            if (lane == 0) {
-                const unsigned int old = atomicAdd(consumed, 1u);
-                if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
-                    issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
+            if (kSplit != 2 && lane == 0) {
+                if (kSplit) {
+                    const unsigned int old = atomicAdd(consumed_o, 1u);
+                    if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
+                        issue_bsk_half(bsk_s, a.bsk, i + 1, 1, bsk_bar_o);
+                } else {
+                    const unsigned int old = atomicAdd(consumed, 1u);
+                    if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
+                        issue_bsk_slice(bsk_s, a.bsk, i + 1, bsk_bar);
+                }
             }
             PBS5_TS(8);
             inv1024_rest(zr, zi, tb_own, tw, lane);   // (its transposition reads are complete before its second pass starts)
