@@ -452,8 +452,16 @@ __global__ void __launch_bounds__(kCts * 64, 1) pbs_kernel5(const PbsArgs a) {
             if (lane == 0) mbar_arrive(bar_full);
             if (kSplit && lane == 0) {   // this warp is done with the diagonal half; the last of the CTA's warps refills it
                 const unsigned int old = atomicAdd(consumed, 1u);
-                if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n)
+                if (old == (unsigned int)(i + 1) * n_act_warps - 1u && i + 1 < a.n) {
                     issue_bsk_half(bsk_s, a.bsk, i + 1, 0, bsk_bar);
+#ifdef B200TFHE_LAB_BSKLAT   // development: latency of the refill, measured by spinning on the barrier (perturbs the kernel)
+                    if (a.dbg && blockIdx.x < 8 && i >= 100 && i < 116) {
+                        const long long t0 = clock64();
+                        mbar_wait(bsk_bar, (uint32_t)((i + 1) & 1));
+                        a.dbg[blockIdx.x * 16 + (i - 100)] = clock64() - t0;
+                    }
+#endif
+                }
             }
             if (dephase) {
                 if (!late) bar_arrive(5, 256);
