@@ -258,12 +258,12 @@ int launch_ks(b200tfhe_ctx *ctx, DevCtx &d, const uint64_t *d_in, uint64_t *d_ou
 
 // Ciphertexts per CTA of the specialised kernels (one CTA per SM).  One launch with c ciphertexts per CTA takes a whole
 // number of waves of t(c) each; measured on this pool's B200 per wave: 3.25 ms for 1 per SM (pbs_lat4_kernel: four warps per
-// polynomial), 4.6 ms for 2 (pbs_lat_kernel<2>: two warps per polynomial), 6.35 ms for 3 and 6.75 ms for 4 (pbs_kernel5).
+// polynomial), 4.7 ms for 2 (pbs_lat_kernel<2>: two warps per polynomial), 6.1 ms for 3 and 6.47 ms for 4 (pbs_kernel5).
 // A batch is served either by ONE launch with the fewest ciphertexts per CTA that still fits it into the minimum number of
 // waves, or by a launch of full 4-per-SM waves followed by a second launch for the remainder with the kernel that suits the
-// remainder (700 = 592 + 108: 6.75 + 3.25 ms instead of two waves of 3 per SM = 12.7 ms) -- whichever the wave model says is
+// remainder (700 = 592 + 108: 6.47 + 3.25 ms instead of two waves of 3 per SM = 12.2 ms) -- whichever the wave model says is
 // shorter.
-struct PbsWaveModel { double t1 = 3.25, t2 = 4.6, t3 = 6.35, t4 = 6.75, split_penalty = 0.15; };
+struct PbsWaveModel { double t1 = 3.25, t2 = 4.7, t3 = 6.1, t4 = 6.47, split_penalty = 0.15; };
 inline int pbs_per_cta(long long batch, long long sms) {
     const long long waves = (batch + 4 * sms - 1) / (4 * sms);
     return (int)((batch + waves * sms - 1) / (waves * sms));
